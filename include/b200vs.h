@@ -1,0 +1,153 @@
+/*
+ * b200vs.h -- C-ABI of the B200-native exact vector-search engine (libb200vs.so).
+ *
+ * The reference (Theseus-AT/mlx-vector-db) has NO FFI for this path: its boundary is the
+ * Python class `MLXVectorStore` (service/optimized_vector_store.py:59-246) and the module
+ * functions of performance/mlx_optimized.py:26-287, whose arithmetic is delegated to
+ * `mlx.core` (mx.matmul / mx.argsort / mx.linalg.norm / mx.concatenate).  Each entry point
+ * below replaces one of those delegation sites; the Python layer in
+ * `mlx-vector-db_b200/b200vs/` binds them with ctypes and re-creates the reference's
+ * class / function surface on top.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns an int status (VS_OK == 0) unless stated; on failure
+ *     `vs_last_error()` returns a thread-local message;
+ *   - "device pointer" = CUDA device memory on the store's device; `stream` is a
+ *     `cudaStream_t` passed as void* (NULL = the legacy default stream);
+ *   - ids are int32 row numbers in insertion order (the reference surfaces uint32 from
+ *     mx.argsort as Python ints); unused output slots hold id -1 and score 0;
+ *   - result order: cosine / dot_product descending score, euclidean ascending distance,
+ *     equal scores -> lower id first (stable argsort of the negated scores,
+ *     service/optimized_vector_store.py:176-181);
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point
+ *     fails with VS_ERR_CUDA.
+ */
+#ifndef B200VS_H
+#define B200VS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_API __attribute__((visibility("default")))
+
+/* status codes -> Python exceptions (see b200vs/_cabi.py) */
+#define VS_OK            0
+#define VS_ERR_INVALID   1   /* bad argument            -> ValueError   */
+#define VS_ERR_CUDA      2   /* CUDA runtime failure    -> RuntimeError */
+#define VS_ERR_OOM       3   /* device memory exhausted -> MemoryError  */
+#define VS_ERR_STATE     4   /* e.g. metric unsupported -> RuntimeError */
+
+/* metric: service/optimized_vector_store.py:211-213, service/models.py:23-27 */
+#define VS_METRIC_COSINE     0
+#define VS_METRIC_EUCLIDEAN  1
+#define VS_METRIC_DOT        2
+
+/* shadow copy of the database scanned by the low-precision candidate kernels */
+#define VS_SHADOW_NONE  0
+#define VS_SHADOW_BF16  1
+
+/* search flags */
+#define VS_SEARCH_AUTO        0   /* choose by batch size                                   */
+#define VS_SEARCH_SCAN_FP32   1   /* K2: fp32 streaming scan (exact)                        */
+#define VS_SEARCH_SCAN_BF16   2   /* K2 over the bf16 shadow + K5 fp32 rescoring (recall)   */
+#define VS_SEARCH_GEMM        3   /* K3: tcgen05 bf16 GEMM candidates + K5 rescoring,
+                                     certified exact with fp32 fallback                      */
+#define VS_SEARCH_GEMM_NOCERT 4   /* K3 + K5 without certification (recall reported)        */
+#define VS_SEARCH_MODE_MASK   0xff
+#define VS_SEARCH_TMA         0x100  /* K2 variant: cp.async.bulk (TMA) staged tiles        */
+#define VS_SEARCH_LDG         0x200  /* K2 variant: direct 128-bit global loads             */
+
+typedef struct vs_store vs_store;
+
+/* Library / device ---------------------------------------------------------------- */
+
+/* Thread-local message for the last failing call on this thread. Never NULL. */
+VS_API const char* vs_last_error(void);
+/* Library version string. */
+VS_API const char* vs_version(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+VS_API int64_t vs_launch_count(void);
+
+/* Store lifetime -- replaces MLXVectorStore.__init__/_create_empty_store
+ * (service/optimized_vector_store.py:60-94): one flat (N, D) fp32 array, here resident in HBM
+ * in a growable virtual-memory arena with pre-computed row norms.
+ *   max_rows: upper bound used to reserve address space (0 = derive from device memory). */
+VS_API int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows,
+                     vs_store** out);
+VS_API int vs_destroy(vs_store* s);
+
+/* K1 append_norm -- replaces `mx.concatenate([self._vectors, new])` + `mx.eval`
+ * (service/optimized_vector_store.py:98-106) and the per-query re-normalisation of the whole
+ * database (:34-38).  Copies `m` rows of `dim` fp32 (row-major, contiguous) to the end of the
+ * store, computes max(||x||, 1e-8) and ||x||^2 per row and the optional bf16 shadow.
+ *   rows_on_device: 0 = host pointer (copied by the library), 1 = device pointer.
+ * Rows become visible to searches enqueued after this call returns. */
+VS_API int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device,
+                     void* stream);
+
+/* self._vector_count (service/optimized_vector_store.py:105) */
+VS_API int64_t vs_count(const vs_store* s);
+/* in-memory part of MLXVectorStore.clear() (:198-209): forget all rows, keep the arena */
+VS_API int vs_reset(vs_store* s);
+/* bytes of device memory currently mapped for this store (get_stats()['memory_usage_mb']) */
+VS_API int64_t vs_memory_bytes(const vs_store* s);
+
+/* Copy rows [first, first+m) of the fp32 master copy to `out` (device or host pointer);
+ * serves persistence (`_save_store`, :218-223) and the filtered-subset gather (:167). */
+VS_API int vs_read_rows(vs_store* s, int64_t first, int64_t m, float* out, int out_on_device,
+                        void* stream);
+
+/* K2/K3 (+K4 merge, +K5 rescoring) -- replaces
+ *   _compiled_cosine_similarity / _compiled_euclidean_distance + mx.argsort(...)[:k] + gather
+ *   (service/optimized_vector_store.py:31-48,176-184) for B == 1, and
+ *   compute_cosine_similarity_batch + mx.argsort(axis=1)[:, :k]
+ *   (performance/mlx_optimized.py:59-88,217-248) for B > 1.
+ * q: (B, dim) fp32 row-major DEVICE pointer.  out_scores / out_ids: (B, k) DEVICE pointers.
+ * Row b holds min(k, count) results, best first; remaining slots id -1.
+ * `row_mask` (nullable): device bitmap, bit i of word i/32 set = row i takes part
+ * (the metadata filter of :159-167 pushed into the scan). */
+VS_API int vs_search(vs_store* s, const float* q, int B, int k, int flags,
+                     const uint32_t* row_mask, float* out_scores, int32_t* out_ids,
+                     void* stream);
+
+/* Same with HOST buffers: H2D of the queries, search, D2H of the results, stream
+ * synchronised on return.  This is the call MLXVectorStore.query()/batch_query() make. */
+VS_API int vs_search_host(vs_store* s, const float* q_host, int B, int k, int flags,
+                          const uint32_t* row_mask_dev, float* out_scores_host,
+                          int32_t* out_ids_host);
+
+/* Per-query certification flags of the last VS_SEARCH_GEMM call on this store/stream are
+ * folded into the result (uncertified queries are re-run exactly); this returns how many
+ * queries took the exact fallback in total since creation (diagnostic). */
+VS_API int64_t vs_fallback_count(const vs_store* s);
+
+/* K4 merge_topk -- new (the reference is single-device): merge G candidate lists of k
+ * entries per query, laid out (G, B, k), into (B, k).  Entries with id < 0 are ignored.
+ * Used after the NCCL all-gather of per-GPU local results. */
+VS_API int vs_merge(int device, int metric, const float* cand_scores, const int32_t* cand_ids,
+                    int G, int B, int k, float* out_scores, int32_t* out_ids, void* stream);
+
+/* K5 rescore_fp32 -- exact fp32 scores (same arithmetic as the fp32 scan) for `kc`
+ * candidate ids per query, sorted, best `k` written out.  cand_ids: (B, kc) device. */
+VS_API int vs_rescore(vs_store* s, const float* q, int B, const int32_t* cand_ids, int kc,
+                      int k, float* out_scores, int32_t* out_ids, void* stream);
+
+/* Stand-alone helpers mirroring performance/mlx_optimized.py on device arrays ------- */
+
+/* normalize_vectors (:110-125): out[i,:] = x[i,:] / max(||x[i,:]||, 1e-8) */
+VS_API int vs_normalize_rows(int device, const float* x, int64_t n, int dim, float* out,
+                             void* stream);
+/* full (B, N) score matrix -- compute_cosine_similarity_{single,batch} (:26-88),
+ * compute_euclidean_distance (:139-148), compute_dot_product (:150-156).
+ * For API parity only; the search path never materialises this matrix. */
+VS_API int vs_score_matrix(int device, int metric, const float* q, int B, const float* db,
+                           int64_t n, int dim, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VS_H */

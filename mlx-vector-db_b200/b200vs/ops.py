@@ -1,0 +1,289 @@
+"""Function surface of the reference's performance/mlx_optimized.py on torch CUDA tensors.
+
+Same names, argument meaning and ValueError behaviour as the reference
+(performance/mlx_optimized.py:26-287); `torch.Tensor` stands in for `mx.array`.  Index
+results are int32 (the reference surfaces uint32 from mx.argsort).  Everything runs in the
+sm_100a kernels of libb200vs; inputs that are not CUDA tensors are moved to the GPU first.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import threading
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import torch
+
+from . import _cabi
+
+logger = logging.getLogger("b200vs.ops")
+
+
+def _dev(x, device=None) -> torch.Tensor:
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+    if not t.is_cuda:
+        t = t.to(device if device is not None else "cuda")
+    return t.to(torch.float32).contiguous()
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: torch.Tensor):
+    return C.c_void_p(t.data_ptr())
+
+
+def _score_matrix(metric: int, q2d: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
+    B, N = q2d.shape[0], db.shape[0]
+    out = torch.empty((B, N), dtype=torch.float32, device=db.device)
+    if B and N:
+        _cabi.check(_cabi.lib().vs_score_matrix(db.device.index or 0, metric, _ptr(q2d), B, _ptr(db),
+                                                N, db.shape[1], _ptr(out), _stream(db)))
+    return out
+
+
+def compute_cosine_similarity_single(query_vector, db_vectors) -> torch.Tensor:
+    """performance/mlx_optimized.py:26-57 -> (N,) similarities."""
+    db = _dev(db_vectors)
+    q = _dev(query_vector, db.device)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    elif not (q.ndim == 2 and q.shape[0] == 1):
+        raise ValueError(f"query_vector must be 1-D or 2-D with one row, got shape {tuple(q.shape)}")
+    return _score_matrix(_cabi.METRIC_COSINE, q, db).flatten()
+
+
+def compute_cosine_similarity_batch(query_vectors, db_vectors) -> torch.Tensor:
+    """performance/mlx_optimized.py:59-88 -> (B, N).  API parity only: the search functions
+    below never materialise this matrix."""
+    db = _dev(db_vectors)
+    q = _dev(query_vectors, db.device)
+    if q.ndim != 2:
+        raise ValueError(f"query_vectors must be 2-D, got shape {tuple(q.shape)}")
+    if db.ndim != 2:
+        raise ValueError(f"db_vectors must be 2-D, got shape {tuple(db.shape)}")
+    if q.shape[1] != db.shape[1]:
+        raise ValueError(f"dimension mismatch: query_vectors {q.shape[1]}, db_vectors {db.shape[1]}")
+    return _score_matrix(_cabi.METRIC_COSINE, q, db)
+
+
+def compute_euclidean_distance(query_vector, db_vectors) -> torch.Tensor:
+    """performance/mlx_optimized.py:139-148."""
+    db = _dev(db_vectors)
+    q = _dev(query_vector, db.device)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    return _score_matrix(_cabi.METRIC_EUCLIDEAN, q, db).flatten()
+
+
+def compute_dot_product(query_vector, db_vectors) -> torch.Tensor:
+    """performance/mlx_optimized.py:150-156."""
+    db = _dev(db_vectors)
+    q = _dev(query_vector, db.device)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    return _score_matrix(_cabi.METRIC_DOT, q, db).flatten()
+
+
+def normalize_vectors(vectors) -> torch.Tensor:
+    """performance/mlx_optimized.py:110-125."""
+    v = _dev(vectors)
+    if v.ndim != 2:
+        raise ValueError(f"vectors must be 2-D for normalisation, got shape {tuple(v.shape)}")
+    if v.shape[0] == 0:
+        return v.clone()
+    out = torch.empty_like(v)
+    _cabi.check(_cabi.lib().vs_normalize_rows(v.device.index or 0, _ptr(v), v.shape[0], v.shape[1],
+                                              _ptr(out), _stream(v)))
+    return out
+
+
+def fast_vector_concatenation(existing_vectors, new_vectors) -> torch.Tensor:
+    """performance/mlx_optimized.py:127-137."""
+    a = _dev(existing_vectors)
+    b = _dev(new_vectors, a.device)
+    if a.shape[0] == 0:
+        return b
+    if b.shape[0] == 0:
+        return a
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("dimensions of the vectors to concatenate differ")
+    return torch.cat([a, b], dim=0)
+
+
+def optimized_vector_addition(existing_vectors, new_vectors, normalize: bool = False) -> torch.Tensor:
+    """performance/mlx_optimized.py:250-255."""
+    combined = fast_vector_concatenation(existing_vectors, new_vectors)
+    return normalize_vectors(combined) if normalize else combined
+
+
+def fast_top_k_indices(scores, k: int) -> torch.Tensor:
+    """performance/mlx_optimized.py:90-108: indices of the k largest scores, best first,
+    ties -> lower index (K4 merge kernel over the score vector)."""
+    if not isinstance(scores, torch.Tensor) or scores.ndim != 1:
+        raise ValueError("scores must be a 1-D tensor")
+    s = _dev(scores)
+    if k <= 0 or s.shape[0] == 0:
+        return torch.zeros((0,), dtype=torch.int32, device=s.device)
+    kk = min(int(k), s.shape[0])
+    ids = torch.arange(s.shape[0], dtype=torch.int32, device=s.device)
+    out_s = torch.empty((kk,), dtype=torch.float32, device=s.device)
+    out_i = torch.empty((kk,), dtype=torch.int32, device=s.device)
+    _cabi.check(_topk_rows(s.reshape(1, -1), kk, out_s, out_i))
+    return out_i
+
+
+def _topk_rows(scores2d: torch.Tensor, kk: int, out_s: torch.Tensor, out_i: torch.Tensor) -> int:
+    """top-kk of each row of a (B, N) score matrix with the K4 merge kernel: pad N up to a
+    multiple of kk and present each row as G lists of kk candidates."""
+    B, N = scores2d.shape
+    G = (N + kk - 1) // kk
+    pad = G * kk - N
+    s = scores2d
+    ids = torch.arange(N, dtype=torch.int32, device=s.device).repeat(B, 1)
+    if pad:
+        s = torch.cat([s, torch.full((B, pad), float("-inf"), device=s.device)], dim=1)
+        ids = torch.cat([ids, torch.full((B, pad), -1, dtype=torch.int32, device=s.device)], dim=1)
+    # vs_merge wants (G, B, k)
+    s = s.reshape(B, G, kk).permute(1, 0, 2).contiguous()
+    ids = ids.reshape(B, G, kk).permute(1, 0, 2).contiguous()
+    return _cabi.lib().vs_merge(s.device.index or 0, _cabi.METRIC_DOT, _ptr(s), _ptr(ids), G, B, kk,
+                                _ptr(out_s), _ptr(out_i), _stream(s))
+
+
+# ---------------------------------------------------------------------- search
+class _DbCache:
+    """The functional API receives the raw database on every call (the reference
+    re-normalises it each time, performance/mlx_optimized.py:41-52).  Here the database is
+    ingested once into a native store (K1) and reused while the same tensor is passed."""
+
+    def __init__(self, capacity: int = 2):
+        self.capacity = capacity
+        self.items: "OrderedDict[tuple, C.c_void_p]" = OrderedDict()
+        self.lock = threading.Lock()
+
+    def get(self, db: torch.Tensor) -> C.c_void_p:
+        key = (db.data_ptr(), tuple(db.shape), db._version, db.device.index or 0)
+        with self.lock:
+            h = self.items.get(key)
+            if h is not None:
+                self.items.move_to_end(key)
+                return h
+            h = C.c_void_p()
+            _cabi.check(_cabi.lib().vs_create(key[3], db.shape[1], _cabi.METRIC_COSINE,
+                                              _cabi.SHADOW_BF16, max(int(db.shape[0]), 1),
+                                              C.byref(h)))
+            _cabi.check(_cabi.lib().vs_append(h, _ptr(db), db.shape[0], 1, _stream(db)))
+            self.items[key] = h
+            while len(self.items) > self.capacity:
+                _, old = self.items.popitem(last=False)
+                _cabi.lib().vs_destroy(old)
+            return h
+
+    def clear(self):
+        with self.lock:
+            for h in self.items.values():
+                _cabi.lib().vs_destroy(h)
+            self.items.clear()
+
+
+_db_cache = _DbCache()
+
+
+def _search(q2d: torch.Tensor, db: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, N = q2d.shape[0], db.shape[0]
+    kk = min(int(k), N)
+    if N == 0 or kk <= 0:
+        return (torch.zeros((B, 0), dtype=torch.int32, device=db.device),
+                torch.zeros((B, 0), dtype=torch.float32, device=db.device))
+    h = _db_cache.get(db)
+    ids = torch.empty((B, kk), dtype=torch.int32, device=db.device)
+    scores = torch.empty((B, kk), dtype=torch.float32, device=db.device)
+    _cabi.check(_cabi.lib().vs_search(h, _ptr(q2d), B, kk, _cabi.SEARCH_AUTO, None, _ptr(scores),
+                                      _ptr(ids), _stream(db)))
+    return ids, scores
+
+
+def optimized_similarity_search(query_vector, db_vectors, k: int = 10):
+    """performance/mlx_optimized.py:199-215 -> (top_k_indices (k,), top_k_scores (k,))."""
+    db = _dev(db_vectors)
+    q = _dev(query_vector, db.device)
+    if q.ndim == 2 and q.shape[0] == 1:
+        q = q.flatten()
+    elif q.ndim != 1:
+        raise ValueError(f"query_vector must be 1-D or 2-D (1 row), shape: {tuple(q.shape)}")
+    if db.ndim != 2 or q.shape[0] != db.shape[1]:
+        raise ValueError(f"dimension mismatch: query {tuple(q.shape)}, db {tuple(db.shape)}")
+    ids, scores = _search(q.reshape(1, -1), db, k)
+    return ids[0], scores[0]
+
+
+def optimized_batch_similarity_search(query_vectors, db_vectors, k: int = 10):
+    """performance/mlx_optimized.py:217-248 -> (indices (B, k), scores (B, k)); the (B, N)
+    score matrix, its negated copy and the full argsort of the reference are never built."""
+    db = _dev(db_vectors)
+    q = _dev(query_vectors, db.device)
+    if q.ndim != 2:
+        raise ValueError(f"query_vectors must be 2-D, got shape {tuple(q.shape)}")
+    if db.ndim != 2:
+        raise ValueError(f"db_vectors must be 2-D, got shape {tuple(db.shape)}")
+    if q.shape[1] != db.shape[1]:
+        raise ValueError(f"dimension mismatch: query_vectors {q.shape[1]}, db_vectors {db.shape[1]}")
+    return _search(q, db, k)
+
+
+# ---------------------------------------------------------------------- monitor / warm-up
+class PerformanceMonitor:
+    """performance/mlx_optimized.py:159-196."""
+
+    def __init__(self):
+        self.call_counts: Dict[str, int] = {}
+        self.total_times: Dict[str, float] = {}
+        self._lock = threading.Lock()
+
+    def record_call(self, func_name: str, duration: float):
+        with self._lock:
+            self.call_counts[func_name] = self.call_counts.get(func_name, 0) + 1
+            self.total_times[func_name] = self.total_times.get(func_name, 0.0) + duration
+
+    def get_stats(self) -> dict:
+        with self._lock:
+            stats = {}
+            for name, calls in self.call_counts.items():
+                if calls == 0:
+                    continue
+                avg = self.total_times[name] / calls
+                stats[name] = {"calls": calls,
+                               "total_time_seconds": round(self.total_times[name], 4),
+                               "avg_time_ms": round(avg * 1000, 4),
+                               "calls_per_second": round(1.0 / avg if avg > 0 else 0, 2)}
+            return stats
+
+    def reset(self):
+        with self._lock:
+            self.call_counts.clear()
+            self.total_times.clear()
+
+
+performance_monitor = PerformanceMonitor()
+
+
+def warmup_compiled_functions(dimension: int = 384, n_vectors: int = 100):
+    """performance/mlx_optimized.py:257-287: run every function once."""
+    try:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        db = torch.randn((max(n_vectors, 1), dimension), generator=g, device="cuda")
+        q1 = torch.randn((dimension,), generator=g, device="cuda")
+        qb = torch.randn((min(10, max(n_vectors, 1)), dimension), generator=g, device="cuda")
+        if n_vectors > 0:
+            compute_cosine_similarity_single(q1, db)
+            compute_cosine_similarity_batch(qb, db)
+            fast_top_k_indices(torch.randn((n_vectors,), generator=g, device="cuda"),
+                               min(5, n_vectors))
+        normalize_vectors(db)
+        fast_vector_concatenation(db[: n_vectors // 2], db[n_vectors // 2:])
+        torch.cuda.synchronize()
+    except Exception as e:  # reference logs and carries on
+        logger.error("warm-up failed: %s", e, exc_info=True)

@@ -1,0 +1,286 @@
+// K4 merge_topk, K5 rescore_fp32 and the small API-parity helpers (normalize_rows,
+// score_matrix).
+#include "scan_topk.cuh"
+
+namespace vs {
+
+constexpr int kMergeCap = 2048;     // candidates sorted in shared memory
+constexpr int kMergeThreads = 256;
+
+// One CTA per query.  Candidates at or above the pruning threshold are compacted into shared
+// memory and bitonic-sorted by (key desc, id asc); if more than kMergeCap survive (mass
+// ties), fall back to k selection passes over global memory (always correct).
+__global__ void __launch_bounds__(kMergeThreads)
+merge_topk_kernel(const float* __restrict__ ck, const int32_t* __restrict__ ci, int64_t per_query,
+                  int k, const uint32_t* __restrict__ tau, int negate, float* __restrict__ out_s,
+                  int32_t* __restrict__ out_i, int64_t out_stride) {
+  __shared__ float sk[kMergeCap];
+  __shared__ int si[kMergeCap];
+  __shared__ int cnt;
+  __shared__ float red_k[kMergeThreads / 32];
+  __shared__ int red_i[kMergeThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* keys = ck + (int64_t)b * per_query;
+  const int32_t* ids = ci + (int64_t)b * per_query;
+  float* os = out_s + (int64_t)b * out_stride;
+  int32_t* oi = out_i + (int64_t)b * out_stride;
+  const float thr = tau ? dec_key(tau[b]) : VS_NEG_INF;
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  for (int64_t i = tid; i < per_query; i += kMergeThreads) {
+    const int id = ids[i];
+    const float key = keys[i];
+    if (id >= 0 && key >= thr) {
+      const int pos = atomicAdd(&cnt, 1);
+      if (pos < kMergeCap) { sk[pos] = key; si[pos] = id; }
+    }
+  }
+  __syncthreads();
+  const int n = cnt;
+  int written = 0;
+  if (n <= kMergeCap) {
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + tid; i < n2; i += kMergeThreads) { sk[i] = VS_NEG_INF; si[i] = VS_ID_SENTINEL; }
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < n2; i += kMergeThreads) {
+          const int j = i ^ stride;
+          if (j > i) {
+            const bool fwd = (i & size) == 0;
+            const float ka = sk[i], kb = sk[j];
+            const int ia = si[i], ib = si[j];
+            const bool swap = fwd ? better(kb, ib, ka, ia) : better(ka, ia, kb, ib);
+            if (swap) { sk[i] = kb; si[i] = ib; sk[j] = ka; si[j] = ia; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    written = n < k ? n : k;
+    for (int i = tid; i < written; i += kMergeThreads) {
+      os[i] = negate ? -sk[i] : sk[i];
+      oi[i] = si[i];
+    }
+  } else {
+    // selection passes: next = best candidate strictly worse than the previous pick
+    float last_k = __int_as_float(0x7f800000);  // +inf
+    int last_i = -1;
+    for (int j = 0; j < k; ++j) {
+      float bk = VS_NEG_INF;
+      int bi = VS_ID_SENTINEL;
+      for (int64_t i = tid; i < per_query; i += kMergeThreads) {
+        const int id = ids[i];
+        const float key = keys[i];
+        if (id >= 0 && key >= thr && better(last_k, last_i, key, id) && better(key, id, bk, bi)) {
+          bk = key; bi = id;
+        }
+      }
+      for (int off = 16; off; off >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
+        const int oi2 = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (better(ok, oi2, bk, bi)) { bk = ok; bi = oi2; }
+      }
+      if ((tid & 31) == 0) { red_k[tid >> 5] = bk; red_i[tid >> 5] = bi; }
+      __syncthreads();
+      bk = red_k[0]; bi = red_i[0];
+      for (int w = 1; w < kMergeThreads / 32; ++w)
+        if (better(red_k[w], red_i[w], bk, bi)) { bk = red_k[w]; bi = red_i[w]; }
+      __syncthreads();
+      if (bi == VS_ID_SENTINEL) break;
+      if (tid == 0) { os[j] = negate ? -bk : bk; oi[j] = bi; }
+      last_k = bk; last_i = bi;
+      written = j + 1;
+    }
+  }
+  for (int64_t i = written + tid; i < out_stride; i += kMergeThreads) { os[i] = 0.f; oi[i] = -1; }
+}
+
+int launch_merge(const float* cand_key, const int32_t* cand_id, int64_t per_query, int B, int k,
+                 const uint32_t* tau, int negate_scores, float* out_scores, int32_t* out_ids,
+                 int64_t out_stride, cudaStream_t stream) {
+  if (B <= 0) return VS_OK;
+  merge_topk_kernel<<<B, kMergeThreads, 0, stream>>>(cand_key, cand_id, per_query, k, tau,
+                                                     negate_scores, out_scores, out_ids, out_stride);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
+}
+
+// K5: one warp per (query, candidate); same accumulation order as the fp32 scan, so the key
+// is bit-identical to what K2 computes for that row.
+__global__ void __launch_bounds__(256)
+rescore_kernel(const float4* __restrict__ rows, int nvec, const float* __restrict__ norms,
+               int metric, const float4* __restrict__ q, int qstride, int B,
+               const int32_t* __restrict__ cand, int kc, float* __restrict__ keys) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)B * kc) return;
+  const int b = (int)(w / kc);
+  const int id = cand[w];
+  if (id < 0) { if (lane == 0) keys[w] = VS_NEG_INF; return; }
+  const float4* x = rows + (int64_t)id * nvec;
+  const float4* qq = q + (int64_t)b * qstride;
+  float acc = 0.f;
+  if (metric == VS_METRIC_EUCLIDEAN) {
+    for (int c = lane; c < nvec; c += 32) acc = sqdiff4_acc(acc, ldg_stream(x + c), qq[c]);
+  } else {
+    for (int c = lane; c < nvec; c += 32) acc = dot4_acc(acc, ldg_stream(x + c), qq[c]);
+  }
+  const float tot = warp_sum(acc);
+  float key;
+  if (metric == VS_METRIC_COSINE) key = tot / __ldg(norms + id);
+  else if (metric == VS_METRIC_EUCLIDEAN) key = -sqrtf(tot);
+  else key = tot;
+  if (lane == 0) keys[w] = key;
+}
+
+int launch_rescore(const float* rows, int ld, int dim, const float* norms, int metric,
+                   const float* qprep, int ldq, int B, const int32_t* cand_ids, int kc,
+                   float* cand_keys_out, cudaStream_t stream) {
+  (void)dim;
+  const int64_t warps = (int64_t)B * kc;
+  if (warps <= 0) return VS_OK;
+  const int64_t blocks = (warps + 7) / 8;
+  rescore_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(rows), ld / 4, norms, metric,
+      reinterpret_cast<const float4*>(qprep), ldq / 4, B, cand_ids, kc, cand_keys_out);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
+}
+
+// ------------------------------------------------ API-parity helpers (not the hot path)
+__global__ void normalize_rows_kernel(const float* __restrict__ x, int64_t n, int dim,
+                                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const float* s = x + r * dim;
+  float acc = 0.f;
+  for (int c = lane; c < dim; c += 32) acc = fmaf(s[c], s[c], acc);
+  const float nrm = fmaxf(sqrtf(warp_sum(acc)), 1e-8f);
+  for (int c = lane; c < dim; c += 32) out[r * dim + c] = s[c] / nrm;
+}
+
+// out[b, r]: one warp per (row r, all B queries in turn); queries are prepared (normalised
+// for cosine) by prep_queries.
+__global__ void score_matrix_kernel(const float* __restrict__ q, int ldq, int B,
+                                    const float* __restrict__ db, int64_t n, int dim, int metric,
+                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const float* x = db + r * dim;
+  float nrm = 1.f;
+  if (metric == VS_METRIC_COSINE) {
+    float a = 0.f;
+    for (int c = lane; c < dim; c += 32) a = fmaf(x[c], x[c], a);
+    nrm = fmaxf(sqrtf(warp_sum(a)), 1e-8f);
+  }
+  for (int b = 0; b < B; ++b) {
+    const float* qq = q + (int64_t)b * ldq;
+    float acc = 0.f;
+    if (metric == VS_METRIC_EUCLIDEAN) {
+      for (int c = lane; c < dim; c += 32) { const float d = x[c] - qq[c]; acc = fmaf(d, d, acc); }
+    } else {
+      for (int c = lane; c < dim; c += 32) acc = fmaf(x[c], qq[c], acc);
+    }
+    const float tot = warp_sum(acc);
+    float v = tot;
+    if (metric == VS_METRIC_COSINE) v = tot / nrm;
+    else if (metric == VS_METRIC_EUCLIDEAN) v = sqrtf(tot);
+    if (lane == 0) out[(int64_t)b * n + r] = v;
+  }
+}
+
+__global__ void regroup_kernel(const float* __restrict__ s, const int32_t* __restrict__ ids, int G,
+                               int B, int k, int negate, float* __restrict__ tk,
+                               int32_t* __restrict__ ti) {
+  const int64_t total = (int64_t)G * B * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % k);
+    const int b = (int)((i / k) % B);
+    const int g = (int)(i / ((int64_t)k * B));
+    const int64_t o = ((int64_t)b * G + g) * k + e;
+    tk[o] = negate ? -s[i] : s[i];
+    ti[o] = ids[i];
+  }
+}
+
+// (G, B, k) reference-convention scores -> (B, G*k) keys
+static int launch_regroup(const float* s, const int32_t* ids, int G, int B, int k, int negate,
+                          float* tk, int32_t* ti, cudaStream_t stream) {
+  const int64_t total = (int64_t)G * B * k;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  regroup_kernel<<<blocks, 256, 0, stream>>>(s, ids, G, B, k, negate, tk, ti);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+int vs_merge(int device, int metric, const float* cand_scores, const int32_t* cand_ids, int G,
+             int B, int k, float* out_scores, int32_t* out_ids, void* stream_) {
+  VS_REQUIRE(G >= 1 && B >= 0 && k >= 0, "G >= 1, B >= 0, k >= 0 required");
+  VS_REQUIRE(metric >= 0 && metric <= 2, "bad metric");
+  if (B == 0 || k == 0) return VS_OK;
+  VS_REQUIRE(cand_scores && cand_ids && out_scores && out_ids, "NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VS_CUDA(cudaSetDevice(device));
+  // candidates arrive as (G, B, k) scores in reference convention (euclidean: distances);
+  // regroup them per query as keys (B, G*k) for the merge kernel.
+  float* tk = nullptr;
+  int32_t* ti = nullptr;
+  const size_t total = (size_t)G * B * k;
+  VS_CUDA(cudaMallocAsync((void**)&tk, total * 4, stream));
+  VS_CUDA(cudaMallocAsync((void**)&ti, total * 4, stream));
+  int rc = launch_regroup(cand_scores, cand_ids, G, B, k, metric == VS_METRIC_EUCLIDEAN, tk, ti, stream);
+  if (!rc) rc = launch_merge(tk, ti, (int64_t)G * k, B, k, nullptr, metric == VS_METRIC_EUCLIDEAN,
+                             out_scores, out_ids, k, stream);
+  cudaFreeAsync(tk, stream);
+  cudaFreeAsync(ti, stream);
+  return rc;
+}
+
+int vs_normalize_rows(int device, const float* x, int64_t n, int dim, float* out, void* stream_) {
+  VS_REQUIRE(n >= 0 && dim > 0, "n >= 0 and dim > 0 required");
+  if (n == 0) return VS_OK;
+  VS_REQUIRE(x && out, "NULL pointer");
+  VS_CUDA(cudaSetDevice(device));
+  normalize_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(x, n, dim, out);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
+}
+
+int vs_score_matrix(int device, int metric, const float* q, int B, const float* db, int64_t n,
+                    int dim, float* out, void* stream_) {
+  VS_REQUIRE(B >= 0 && n >= 0 && dim > 0, "bad sizes");
+  VS_REQUIRE(metric >= 0 && metric <= 2, "bad metric");
+  if (B == 0 || n == 0) return VS_OK;
+  VS_REQUIRE(q && db && out, "NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VS_CUDA(cudaSetDevice(device));
+  float* qp = nullptr;
+  VS_CUDA(cudaMallocAsync((void**)&qp, (size_t)B * dim * 4, stream));
+  int rc = launch_prep_queries(q, B, dim, metric, dim, false, 1.f, qp, nullptr, nullptr, stream);
+  if (!rc) {
+    score_matrix_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(qp, dim, B, db, n, dim, metric, out);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "score_matrix_kernel", __FILE__, __LINE__);
+  }
+  cudaFreeAsync(qp, stream);
+  return rc;
+}
+
+}  // extern "C"
+

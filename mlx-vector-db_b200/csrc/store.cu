@@ -1,0 +1,384 @@
+// Store lifetime, HBM arenas and K1 append_norm.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "store.cuh"
+
+namespace vs {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string t_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e),
+           file, line, what);
+  t_error = buf;
+  cudaGetLastError();  // clear the sticky-less error state
+  return e == cudaErrorMemoryAllocation ? VS_ERR_OOM : VS_ERR_CUDA;
+}
+
+// --------------------------------------------------- driver API via cudart
+// libcuda is not linked: the library must load (and export its symbols) on a box without a
+// driver; the entry points are resolved at first use through the runtime.
+struct DriverApi {
+  CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t);
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle);
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+  CUresult (*MemUnmap)(CUdeviceptr, size_t);
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+  CUresult (*GetErrorString)(CUresult, const char**);
+  bool ok = false;
+};
+
+static int load_driver(DriverApi** out) {
+  static DriverApi api;
+  static std::once_flag once;
+  static std::string why;
+  std::call_once(once, [] {
+    struct { const char* name; void** slot; } syms[] = {
+        {"cuMemGetAllocationGranularity", (void**)&api.MemGetAllocationGranularity},
+        {"cuMemAddressReserve", (void**)&api.MemAddressReserve},
+        {"cuMemAddressFree", (void**)&api.MemAddressFree},
+        {"cuMemCreate", (void**)&api.MemCreate},
+        {"cuMemRelease", (void**)&api.MemRelease},
+        {"cuMemMap", (void**)&api.MemMap},
+        {"cuMemUnmap", (void**)&api.MemUnmap},
+        {"cuMemSetAccess", (void**)&api.MemSetAccess},
+        {"cuGetErrorString", (void**)&api.GetErrorString},
+    };
+    for (auto& s : syms) {
+      cudaDriverEntryPointQueryResult q;
+      cudaError_t e = cudaGetDriverEntryPoint(s.name, s.slot, cudaEnableDefault, &q);
+      if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || *s.slot == nullptr) {
+        why = std::string("driver entry point not found: ") + s.name;
+        cudaGetLastError();
+        return;
+      }
+    }
+    api.ok = true;
+  });
+  if (!api.ok) { set_error(why); return VS_ERR_CUDA; }
+  *out = &api;
+  return VS_OK;
+}
+
+static int cu_fail(DriverApi* d, CUresult r, const char* what) {
+  const char* s = nullptr;
+  d->GetErrorString(r, &s);
+  set_error(std::string("driver error in ") + what + ": " + (s ? s : "?"));
+  return r == CUDA_ERROR_OUT_OF_MEMORY ? VS_ERR_OOM : VS_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------- Arena
+int Arena::init(int device, size_t max_bytes) {
+  device_ = device;
+  const char* mode = getenv("B200VS_ARENA");
+  vmm_ = !(mode && strcmp(mode, "malloc") == 0);
+  if (!vmm_) { reserved_ = max_bytes; return VS_OK; }
+  DriverApi* d;
+  if (int rc = load_driver(&d)) return rc;
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  CUresult r = d->MemGetAllocationGranularity(&gran_, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+  if (r != CUDA_SUCCESS) return cu_fail(d, r, "cuMemGetAllocationGranularity");
+  if (gran_ == 0) gran_ = 2u << 20;
+  reserved_ = (size_t)round_up((int64_t)max_bytes, (int64_t)gran_);
+  r = d->MemAddressReserve(&base_, reserved_, 0, 0, 0);
+  if (r != CUDA_SUCCESS) return cu_fail(d, r, "cuMemAddressReserve");
+  return VS_OK;
+}
+
+int Arena::ensure(size_t bytes, cudaStream_t stream) {
+  if (bytes <= mapped_) return VS_OK;
+  if (bytes > reserved_) { set_error("store is full (max_rows reached)"); return VS_ERR_OOM; }
+  if (!vmm_) {
+    size_t want = bytes > mapped_ * 2 ? bytes : mapped_ * 2;
+    if (want > reserved_) want = reserved_;
+    void* p = nullptr;
+    VS_CUDA(cudaMalloc(&p, want));
+    if (base_) {
+      VS_CUDA(cudaMemcpyAsync(p, (void*)base_, mapped_, cudaMemcpyDeviceToDevice, stream));
+      VS_CUDA(cudaStreamSynchronize(stream));
+      VS_CUDA(cudaFree((void*)base_));
+    }
+    base_ = (CUdeviceptr)p;
+    mapped_ = want;
+    return VS_OK;
+  }
+  DriverApi* d;
+  if (int rc = load_driver(&d)) return rc;
+  // grow by at least 25 % (and 64 MB) so a stream of small appends maps few chunks
+  size_t want = bytes;
+  size_t geo = mapped_ + mapped_ / 4;
+  if (geo > want) want = geo;
+  if (want < mapped_ + (64u << 20)) want = mapped_ + (64u << 20);
+  want = (size_t)round_up((int64_t)want, (int64_t)gran_);
+  if (want > reserved_) want = reserved_;
+  size_t chunk = want - mapped_;
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device_;
+  CUmemGenericAllocationHandle h;
+  CUresult r = d->MemCreate(&h, chunk, &prop, 0);
+  if (r != CUDA_SUCCESS && want > (size_t)round_up((int64_t)bytes, (int64_t)gran_)) {
+    // geometric head-room did not fit: retry with exactly what is needed
+    want = (size_t)round_up((int64_t)bytes, (int64_t)gran_);
+    chunk = want - mapped_;
+    r = d->MemCreate(&h, chunk, &prop, 0);
+  }
+  if (r != CUDA_SUCCESS) return cu_fail(d, r, "cuMemCreate");
+  r = d->MemMap(base_ + mapped_, chunk, 0, h, 0);
+  if (r != CUDA_SUCCESS) { d->MemRelease(h); return cu_fail(d, r, "cuMemMap"); }
+  CUmemAccessDesc acc = {};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = device_;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  r = d->MemSetAccess(base_ + mapped_, chunk, &acc, 1);
+  if (r != CUDA_SUCCESS) {
+    d->MemUnmap(base_ + mapped_, chunk);
+    d->MemRelease(h);
+    return cu_fail(d, r, "cuMemSetAccess");
+  }
+  chunks_.push_back({h, chunk});
+  mapped_ = want;
+  return VS_OK;
+}
+
+void Arena::destroy() {
+  if (!vmm_) {
+    if (base_) cudaFree((void*)base_);
+  } else if (base_) {
+    DriverApi* d;
+    if (load_driver(&d) == VS_OK) {
+      size_t off = 0;
+      for (auto& c : chunks_) {
+        d->MemUnmap(base_ + off, c.second);
+        d->MemRelease(c.first);
+        off += c.second;
+      }
+      d->MemAddressFree(base_, reserved_);
+    }
+  }
+  chunks_.clear();
+  base_ = 0;
+  mapped_ = reserved_ = 0;
+}
+
+// --------------------------------------------------------- K1 append_norm
+// One warp per appended row: copy into the master arena (padded stride), row norm with the
+// 1e-8 clamp of service/optimized_vector_store.py:36-38, ||x||^2, optional bf16 shadow row.
+__global__ void __launch_bounds__(256)
+append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
+                   int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
+                   float* __restrict__ sqnorms, __nv_bfloat16* __restrict__ shadow, int ld16,
+                   int normalize_shadow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < m; r += nwarps) {
+    const float* s = src + r * src_ld;
+    float* d = rows + (n0 + r) * (int64_t)ld;
+    const bool in_place = (s == d);
+    float acc = 0.f;
+    for (int c = lane; c < ld; c += 32) {
+      float v = c < dim ? s[c] : 0.f;
+      acc = fmaf(v, v, acc);
+      if (!in_place) d[c] = v;
+    }
+    const float tot = warp_sum(acc);
+    const float nrm = fmaxf(sqrtf(tot), 1e-8f);
+    if (lane == 0) { norms[n0 + r] = nrm; sqnorms[n0 + r] = tot; }
+    if (shadow != nullptr) {
+      __nv_bfloat16* sh = shadow + (n0 + r) * (int64_t)ld16;
+      for (int c = lane; c < ld16; c += 32) {
+        float v = c < dim ? s[c] : 0.f;
+        if (normalize_shadow) v = v / nrm;
+        sh[c] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+// ------------------------------------------------------------------- C-ABI
+extern "C" {
+
+const char* vs_last_error(void) { return t_error.c_str(); }
+const char* vs_version(void) { return "b200vs 0.1 (sm_100a)"; }
+int64_t vs_launch_count(void) { return g_launches.load(); }
+
+int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_store** out) {
+  VS_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  VS_REQUIRE(dim > 0 && dim <= 65536, "dim must be in [1, 65536]");
+  VS_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (cosine), 1 (euclidean) or 2 (dot)");
+  VS_REQUIRE(shadow == VS_SHADOW_NONE || shadow == VS_SHADOW_BF16, "shadow must be 0 or 1");
+  VS_REQUIRE(max_rows >= 0 && max_rows < (int64_t)0x7fffffff, "max_rows must be < 2^31");
+  int ndev = 0;
+  VS_CUDA(cudaGetDeviceCount(&ndev));
+  VS_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+  VS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libb200vs is built for sm_100a (B200) only; device is sm_" +
+              std::to_string(prop.major) + std::to_string(prop.minor));
+    return VS_ERR_STATE;
+  }
+  vs_store* s = new vs_store();
+  s->device = device;
+  s->dim = dim;
+  s->ld = (int)round_up(dim, 4);
+  s->ld16 = (int)round_up(dim, 64);
+  s->metric = metric;
+  s->shadow = shadow;
+  s->num_sms = prop.multiProcessorCount;
+  const size_t row_bytes = (size_t)s->ld * 4 + 8 + (shadow ? (size_t)s->ld16 * 2 : 0);
+  if (max_rows == 0) {
+    max_rows = (int64_t)((double)prop.totalGlobalMem * 0.92 / (double)row_bytes);
+    if (max_rows > 0x7ffffff0) max_rows = 0x7ffffff0;
+  }
+  s->max_rows = max_rows;
+  int rc = s->rows.init(device, (size_t)max_rows * s->ld * 4);
+  if (!rc) rc = s->norms.init(device, (size_t)max_rows * 4);
+  if (!rc) rc = s->sqnorms.init(device, (size_t)max_rows * 4);
+  if (!rc && shadow) rc = s->shadow_rows.init(device, (size_t)max_rows * s->ld16 * 2);
+  if (rc) { vs_destroy(s); return rc; }
+  // keep stream-ordered workspace memory cached in the pool between searches
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+  s->pinned_bytes = 1u << 20;
+  cudaError_t e = cudaEventCreateWithFlags(&s->append_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->pinned_in, s->pinned_bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->pinned_out, s->pinned_bytes);
+  if (e != cudaSuccess) { vs_destroy(s); return cuda_fail(e, "store stream/pinned setup", __FILE__, __LINE__); }
+  *out = s;
+  return VS_OK;
+}
+
+int vs_destroy(vs_store* s) {
+  if (!s) return VS_OK;
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  s->rows.destroy();
+  s->norms.destroy();
+  s->sqnorms.destroy();
+  s->shadow_rows.destroy();
+  if (s->append_done) cudaEventDestroy(s->append_done);
+  if (s->host_stream) cudaStreamDestroy(s->host_stream);
+  if (s->pinned_in) cudaFreeHost(s->pinned_in);
+  if (s->pinned_out) cudaFreeHost(s->pinned_out);
+  delete s;
+  cudaGetLastError();
+  return VS_OK;
+}
+
+int64_t vs_count(const vs_store* s) { return s ? s->count.load(std::memory_order_acquire) : 0; }
+int64_t vs_fallback_count(const vs_store* s) { return s ? s->fallbacks.load() : 0; }
+
+int64_t vs_memory_bytes(const vs_store* s) {
+  if (!s) return 0;
+  return (int64_t)(s->rows.mapped() + s->norms.mapped() + s->sqnorms.mapped() +
+                   s->shadow_rows.mapped());
+}
+
+int vs_reset(vs_store* s) {
+  VS_REQUIRE(s != nullptr, "store is NULL");
+  std::lock_guard<std::mutex> g(s->mu);
+  s->count.store(0, std::memory_order_release);
+  return VS_OK;
+}
+
+int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device, void* stream_) {
+  VS_REQUIRE(s != nullptr, "store is NULL");
+  VS_REQUIRE(m >= 0, "m must be >= 0");
+  if (m == 0) return VS_OK;
+  VS_REQUIRE(rows != nullptr, "rows is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  std::lock_guard<std::mutex> g(s->mu);
+  VS_CUDA(cudaSetDevice(s->device));
+  const int64_t n0 = s->count.load(std::memory_order_acquire);
+  const int64_t n1 = n0 + m;
+  if (n1 > s->max_rows) { set_error("store is full (max_rows reached)"); return VS_ERR_OOM; }
+  if (int rc = s->rows.ensure((size_t)n1 * s->ld * 4, stream)) return rc;
+  if (int rc = s->norms.ensure((size_t)n1 * 4, stream)) return rc;
+  if (int rc = s->sqnorms.ensure((size_t)n1 * 4, stream)) return rc;
+  if (s->shadow)
+    if (int rc = s->shadow_rows.ensure((size_t)n1 * s->ld16 * 2, stream)) return rc;
+
+  float* master = (float*)s->rows.ptr();
+  const int64_t piece = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)s->dim * 4));
+  for (int64_t off = 0; off < m; off += piece) {
+    const int64_t mm = std::min(piece, m - off);
+    const float* src = rows + off * s->dim;
+    float* staging = nullptr;
+    const float* ksrc = src;
+    int64_t ksrc_ld = s->dim;
+    if (!rows_on_device) {
+      if (s->ld == s->dim) {  // land directly in the arena, normalise in place
+        float* dst = master + (n0 + off) * s->ld;
+        VS_CUDA(cudaMemcpyAsync(dst, src, (size_t)mm * s->dim * 4, cudaMemcpyHostToDevice, stream));
+        ksrc = dst;
+        ksrc_ld = s->ld;
+      } else {
+        VS_CUDA(cudaMallocAsync((void**)&staging, (size_t)mm * s->dim * 4, stream));
+        VS_CUDA(cudaMemcpyAsync(staging, src, (size_t)mm * s->dim * 4, cudaMemcpyHostToDevice, stream));
+        ksrc = staging;
+      }
+    }
+    const int warps_per_block = 8;
+    int64_t blocks = (mm + warps_per_block - 1) / warps_per_block;
+    const int64_t cap = (int64_t)s->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    append_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+        ksrc, ksrc_ld, master, s->ld, s->dim, n0 + off, mm, (float*)s->norms.ptr(),
+        (float*)s->sqnorms.ptr(), s->shadow ? (__nv_bfloat16*)s->shadow_rows.ptr() : nullptr,
+        s->ld16, s->metric == VS_METRIC_COSINE ? 1 : 0);
+    count_launch();
+    VS_CHECK_LAUNCH();
+    if (staging) VS_CUDA(cudaFreeAsync(staging, stream));
+  }
+  if (!rows_on_device) VS_CUDA(cudaStreamSynchronize(stream));  // host buffer may be reused
+  // searches on other streams wait for this event before reading the new rows
+  VS_CUDA(cudaEventRecord(s->append_done, stream));
+  s->append_stream = stream;
+  s->count.store(n1, std::memory_order_release);
+  return VS_OK;
+}
+
+int vs_read_rows(vs_store* s, int64_t first, int64_t m, float* out, int out_on_device,
+                 void* stream_) {
+  VS_REQUIRE(s != nullptr, "store is NULL");
+  const int64_t n = s->count.load(std::memory_order_acquire);
+  VS_REQUIRE(first >= 0 && m >= 0 && first + m <= n, "row range out of bounds");
+  if (m == 0) return VS_OK;
+  VS_REQUIRE(out != nullptr, "out is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VS_CUDA(cudaSetDevice(s->device));
+  const float* src = (const float*)s->rows.ptr() + first * s->ld;
+  VS_CUDA(cudaMemcpy2DAsync(out, (size_t)s->dim * 4, src, (size_t)s->ld * 4, (size_t)s->dim * 4,
+                            (size_t)m, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                            stream));
+  if (!out_on_device) VS_CUDA(cudaStreamSynchronize(stream));
+  return VS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Host-side state of one store: growable HBM arenas + row count.
+#pragma once
+#include <cuda.h>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+
+namespace vs {
+
+// A device buffer that grows in place.  Default implementation: CUDA virtual memory
+// management -- one address range reserved up front, physical 2 MB-granular chunks mapped
+// behind it as rows arrive, so the base pointer never changes (kernels in flight and TMA
+// descriptors stay valid; appends never copy the old rows, unlike the reference's
+// mx.concatenate, service/optimized_vector_store.py:102).
+// B200VS_ARENA=malloc selects a cudaMalloc + copy-on-grow arena instead (diagnostic).
+class Arena {
+ public:
+  int init(int device, size_t max_bytes);
+  int ensure(size_t bytes, cudaStream_t stream);   // make [0, bytes) usable
+  void destroy();
+  void* ptr() const { return reinterpret_cast<void*>(base_); }
+  size_t mapped() const { return mapped_; }
+
+ private:
+  int device_ = 0;
+  bool vmm_ = true;
+  CUdeviceptr base_ = 0;
+  size_t reserved_ = 0, mapped_ = 0, gran_ = 0;
+  std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks_;
+};
+
+}  // namespace vs
+
+struct vs_store {
+  int device = 0;
+  int dim = 0;        // D
+  int ld = 0;         // fp32 row stride in floats (D rounded up to 4 -> 16 B aligned rows)
+  int ld16 = 0;       // bf16 shadow row stride in elements (D rounded up to 64 -> 128 B)
+  int metric = 0;
+  int shadow = 0;
+  int num_sms = 148;
+  int64_t max_rows = 0;
+  std::atomic<int64_t> count{0};
+  std::atomic<int64_t> fallbacks{0};
+  std::mutex mu;                 // one writer at a time (append / reset)
+  cudaEvent_t append_done = nullptr;   // recorded after the last append's kernels
+  cudaStream_t append_stream = nullptr;
+  // vs_search_host: private stream + pinned staging, serialised by host_mu
+  std::mutex host_mu;
+  cudaStream_t host_stream = nullptr;
+  void* pinned_in = nullptr;
+  void* pinned_out = nullptr;
+  size_t pinned_bytes = 0;
+  vs::Arena rows;                // fp32 master, (N, ld)
+  vs::Arena norms;               // max(||x||, 1e-8), (N,)
+  vs::Arena sqnorms;             // ||x||^2, (N,)
+  vs::Arena shadow_rows;         // bf16, (N, ld16): x/max(||x||,1e-8) for cosine, x otherwise
+};

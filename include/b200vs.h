@@ -72,6 +72,12 @@ VS_API const char* vs_version(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 VS_API int64_t vs_launch_count(void);
 
+/* Bracket the dominant kernels (kind 0 = K2 scan, 1 = K3 GEMM) with CUDA events on their
+ * launch stream while enabled; vs_profile_read waits for them, returns the summed kernel time
+ * and launch count since the last read, and clears the record.  Measurement aid for bench.py. */
+VS_API int vs_profile(int enable);
+VS_API int vs_profile_read(int kind, double* total_ms, int64_t* launches);
+
 /* Store lifetime -- replaces MLXVectorStore.__init__/_create_empty_store
  * (service/optimized_vector_store.py:60-94): one flat (N, D) fp32 array, here resident in HBM
  * in a growable virtual-memory arena with pre-computed row norms.
@@ -88,6 +94,14 @@ VS_API int vs_destroy(vs_store* s);
  * Rows become visible to searches enqueued after this call returns. */
 VS_API int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device,
                      void* stream);
+
+/* Same for one shard of a row-sharded store: the m rows get the global ids
+ * first_global_id .. first_global_id + m - 1, and searches report global ids.  Global ids
+ * must increase with the local row number so that the tie order (lower id first) of a shard
+ * agrees with the global one.  A store uses either vs_append (ids = local row numbers) or
+ * vs_append_ids throughout. */
+VS_API int vs_append_ids(vs_store* s, const float* rows, int64_t m, int rows_on_device,
+                         int64_t first_global_id, void* stream);
 
 /* self._vector_count (service/optimized_vector_store.py:105) */
 VS_API int64_t vs_count(const vs_store* s);
@@ -126,10 +140,13 @@ VS_API int vs_search_host(vs_store* s, const float* q_host, int B, int k, int fl
 VS_API int64_t vs_fallback_count(const vs_store* s);
 
 /* K4 merge_topk -- new (the reference is single-device): merge G candidate lists of k
- * entries per query, laid out (G, B, k), into (B, k).  Entries with id < 0 are ignored.
- * Used after the NCCL all-gather of per-GPU local results. */
+ * entries per query into (B, k).  Group g's (B, k) block starts at g * group_stride elements
+ * from both base pointers (0 = dense (G, B, k)).  Entries with id < 0 are ignored; scores
+ * are in the reference convention (euclidean: distances).  Used after the NCCL all-gather
+ * of per-GPU local results. */
 VS_API int vs_merge(int device, int metric, const float* cand_scores, const int32_t* cand_ids,
-                    int G, int B, int k, float* out_scores, int32_t* out_ids, void* stream);
+                    int G, int B, int k, int64_t group_stride, float* out_scores,
+                    int32_t* out_ids, void* stream);
 
 /* K5 rescore_fp32 -- exact fp32 scores (same arithmetic as the fp32 scan) for `kc`
  * candidate ids per query, sorted, best `k` written out.  cand_ids: (B, kc) device. */

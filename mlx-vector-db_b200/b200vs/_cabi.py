@@ -46,9 +46,12 @@ def lib() -> C.CDLL:
         "vs_last_error": (C.c_char_p, []),
         "vs_version": (C.c_char_p, []),
         "vs_launch_count": (i64, []),
+        "vs_profile": (i32, [i32]),
+        "vs_profile_read": (i32, [i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
         "vs_create": (i32, [i32, i32, i32, i32, i64, C.POINTER(p)]),
         "vs_destroy": (i32, [p]),
         "vs_append": (i32, [p, f32p, i64, i32, p]),
+        "vs_append_ids": (i32, [p, f32p, i64, i32, i64, p]),
         "vs_count": (i64, [p]),
         "vs_reset": (i32, [p]),
         "vs_memory_bytes": (i64, [p]),
@@ -56,7 +59,7 @@ def lib() -> C.CDLL:
         "vs_search": (i32, [p, f32p, i32, i32, i32, u32p, f32p, i32p, p]),
         "vs_search_host": (i32, [p, f32p, i32, i32, i32, u32p, f32p, i32p]),
         "vs_fallback_count": (i64, [p]),
-        "vs_merge": (i32, [i32, i32, f32p, i32p, i32, i32, i32, f32p, i32p, p]),
+        "vs_merge": (i32, [i32, i32, f32p, i32p, i32, i32, i32, i64, f32p, i32p, p]),
         "vs_rescore": (i32, [p, f32p, i32, i32p, i32, i32, f32p, i32p, p]),
         "vs_normalize_rows": (i32, [i32, f32p, i64, i32, f32p, p]),
         "vs_score_matrix": (i32, [i32, i32, f32p, i32, f32p, i64, i32, f32p, p]),

@@ -149,7 +149,7 @@ def _topk_rows(scores2d: torch.Tensor, kk: int, out_s: torch.Tensor, out_i: torc
     # vs_merge wants (G, B, k)
     s = s.reshape(B, G, kk).permute(1, 0, 2).contiguous()
     ids = ids.reshape(B, G, kk).permute(1, 0, 2).contiguous()
-    return _cabi.lib().vs_merge(s.device.index or 0, _cabi.METRIC_DOT, _ptr(s), _ptr(ids), G, B, kk,
+    return _cabi.lib().vs_merge(s.device.index or 0, _cabi.METRIC_DOT, _ptr(s), _ptr(ids), G, B, kk, 0,
                                 _ptr(out_s), _ptr(out_i), _stream(s))
 
 

@@ -16,6 +16,16 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 extern std::atomic<int64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional CUDA-event bracket around the dominant kernels (vs_profile / vs_profile_read):
+// bench.py uses it to time the scan / GEMM kernel alone on the stream it is launched on.
+enum { kProfScan = 0, kProfGemm = 1, kProfKinds = 2 };
+struct ProfScope {
+  ProfScope(int kind, cudaStream_t stream);
+  ~ProfScope();
+  cudaStream_t stream_;
+  cudaEvent_t stop_ = nullptr;
+};
+
 #define VS_CUDA(expr)                                                        \
   do {                                                                       \
     cudaError_t _e = (expr);                                                 \

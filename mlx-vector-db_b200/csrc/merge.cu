@@ -7,30 +7,46 @@ namespace vs {
 constexpr int kMergeCap = 2048;     // candidates sorted in shared memory
 constexpr int kMergeThreads = 256;
 
-// One CTA per query.  Candidates at or above the pruning threshold are compacted into shared
-// memory and bitonic-sorted by (key desc, id asc); if more than kMergeCap survive (mass
-// ties), fall back to k selection passes over global memory (always correct).
+// One CTA per query.  Candidate i of query b lives at
+//   (i / chunk) * chunk_stride + b * query_stride + (i % chunk)
+// (scan lists: one chunk of nlists*k entries; gathered shard results: G chunks of k).
+// Candidates at or above the pruning threshold are compacted into shared memory and
+// bitonic-sorted by (key desc, id asc); if more than kMergeCap survive (mass ties), fall back
+// to k selection passes over global memory (always correct).  Ids are mapped local -> global
+// (`id_map`) before they are compared, so the tie order is the global one.
+__device__ __forceinline__ int64_t cand_addr(const MergeParams& p, int b, int64_t i) {
+  const int64_t c = i / p.chunk;
+  return c * p.chunk_stride + (int64_t)b * p.query_stride + (i - c * p.chunk);
+}
+__device__ __forceinline__ bool cand_load(const MergeParams& p, int b, int64_t i, float thr,
+                                          float& key, int& id) {
+  const int64_t a = cand_addr(p, b, i);
+  id = p.ci[a];
+  if (id < 0) return false;
+  key = p.ck[a];
+  if (p.negate_in) key = -key;
+  if (!(key >= thr)) return false;
+  if (p.id_map) id = p.id_map[id];
+  return true;
+}
+
 __global__ void __launch_bounds__(kMergeThreads)
-merge_topk_kernel(const float* __restrict__ ck, const int32_t* __restrict__ ci, int64_t per_query,
-                  int k, const uint32_t* __restrict__ tau, int negate, float* __restrict__ out_s,
-                  int32_t* __restrict__ out_i, int64_t out_stride) {
+merge_topk_kernel(const MergeParams p) {
   __shared__ float sk[kMergeCap];
   __shared__ int si[kMergeCap];
   __shared__ int cnt;
   __shared__ float red_k[kMergeThreads / 32];
   __shared__ int red_i[kMergeThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* keys = ck + (int64_t)b * per_query;
-  const int32_t* ids = ci + (int64_t)b * per_query;
-  float* os = out_s + (int64_t)b * out_stride;
-  int32_t* oi = out_i + (int64_t)b * out_stride;
-  const float thr = tau ? dec_key(tau[b]) : VS_NEG_INF;
+  const int k = p.k;
+  float* os = p.out_s + (int64_t)b * p.out_stride;
+  int32_t* oi = p.out_i + (int64_t)b * p.out_stride;
+  const float thr = p.tau ? dec_key(p.tau[b]) : VS_NEG_INF;
   if (tid == 0) cnt = 0;
   __syncthreads();
-  for (int64_t i = tid; i < per_query; i += kMergeThreads) {
-    const int id = ids[i];
-    const float key = keys[i];
-    if (id >= 0 && key >= thr) {
+  for (int64_t i = tid; i < p.per_query; i += kMergeThreads) {
+    float key; int id;
+    if (cand_load(p, b, i, thr, key, id)) {
       const int pos = atomicAdd(&cnt, 1);
       if (pos < kMergeCap) { sk[pos] = key; si[pos] = id; }
     }
@@ -60,7 +76,7 @@ merge_topk_kernel(const float* __restrict__ ck, const int32_t* __restrict__ ci, 
     }
     written = n < k ? n : k;
     for (int i = tid; i < written; i += kMergeThreads) {
-      os[i] = negate ? -sk[i] : sk[i];
+      os[i] = p.negate_out ? -sk[i] : sk[i];
       oi[i] = si[i];
     }
   } else {
@@ -70,10 +86,10 @@ merge_topk_kernel(const float* __restrict__ ck, const int32_t* __restrict__ ci, 
     for (int j = 0; j < k; ++j) {
       float bk = VS_NEG_INF;
       int bi = VS_ID_SENTINEL;
-      for (int64_t i = tid; i < per_query; i += kMergeThreads) {
-        const int id = ids[i];
-        const float key = keys[i];
-        if (id >= 0 && key >= thr && better(last_k, last_i, key, id) && better(key, id, bk, bi)) {
+      for (int64_t i = tid; i < p.per_query; i += kMergeThreads) {
+        float key; int id;
+        if (cand_load(p, b, i, thr, key, id) && better(last_k, last_i, key, id) &&
+            better(key, id, bk, bi)) {
           bk = key; bi = id;
         }
       }
@@ -89,23 +105,32 @@ merge_topk_kernel(const float* __restrict__ ck, const int32_t* __restrict__ ci, 
         if (better(red_k[w], red_i[w], bk, bi)) { bk = red_k[w]; bi = red_i[w]; }
       __syncthreads();
       if (bi == VS_ID_SENTINEL) break;
-      if (tid == 0) { os[j] = negate ? -bk : bk; oi[j] = bi; }
+      if (tid == 0) { os[j] = p.negate_out ? -bk : bk; oi[j] = bi; }
       last_k = bk; last_i = bi;
       written = j + 1;
     }
   }
-  for (int64_t i = written + tid; i < out_stride; i += kMergeThreads) { os[i] = 0.f; oi[i] = -1; }
+  for (int64_t i = written + tid; i < p.out_stride; i += kMergeThreads) { os[i] = 0.f; oi[i] = -1; }
+}
+
+int launch_merge(const MergeParams& p, int B, cudaStream_t stream) {
+  if (B <= 0) return VS_OK;
+  merge_topk_kernel<<<B, kMergeThreads, 0, stream>>>(p);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
 }
 
 int launch_merge(const float* cand_key, const int32_t* cand_id, int64_t per_query, int B, int k,
                  const uint32_t* tau, int negate_scores, float* out_scores, int32_t* out_ids,
-                 int64_t out_stride, cudaStream_t stream) {
-  if (B <= 0) return VS_OK;
-  merge_topk_kernel<<<B, kMergeThreads, 0, stream>>>(cand_key, cand_id, per_query, k, tau,
-                                                     negate_scores, out_scores, out_ids, out_stride);
-  count_launch();
-  VS_CHECK_LAUNCH();
-  return VS_OK;
+                 int64_t out_stride, cudaStream_t stream, const int32_t* id_map) {
+  MergeParams p = {};
+  p.ck = cand_key; p.ci = cand_id;
+  p.per_query = per_query; p.chunk = per_query > 0 ? per_query : 1; p.chunk_stride = 0;
+  p.query_stride = per_query;
+  p.k = k; p.tau = tau; p.negate_in = 0; p.negate_out = negate_scores; p.id_map = id_map;
+  p.out_s = out_scores; p.out_i = out_ids; p.out_stride = out_stride;
+  return launch_merge(p, B, stream);
 }
 
 // K5: one warp per (query, candidate); same accumulation order as the fp32 scan, so the key
@@ -195,32 +220,6 @@ __global__ void score_matrix_kernel(const float* __restrict__ q, int ldq, int B,
   }
 }
 
-__global__ void regroup_kernel(const float* __restrict__ s, const int32_t* __restrict__ ids, int G,
-                               int B, int k, int negate, float* __restrict__ tk,
-                               int32_t* __restrict__ ti) {
-  const int64_t total = (int64_t)G * B * k;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int e = (int)(i % k);
-    const int b = (int)((i / k) % B);
-    const int g = (int)(i / ((int64_t)k * B));
-    const int64_t o = ((int64_t)b * G + g) * k + e;
-    tk[o] = negate ? -s[i] : s[i];
-    ti[o] = ids[i];
-  }
-}
-
-// (G, B, k) reference-convention scores -> (B, G*k) keys
-static int launch_regroup(const float* s, const int32_t* ids, int G, int B, int k, int negate,
-                          float* tk, int32_t* ti, cudaStream_t stream) {
-  const int64_t total = (int64_t)G * B * k;
-  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  regroup_kernel<<<blocks, 256, 0, stream>>>(s, ids, G, B, k, negate, tk, ti);
-  count_launch();
-  VS_CHECK_LAUNCH();
-  return VS_OK;
-}
-
 }  // namespace vs
 
 using namespace vs;
@@ -228,26 +227,26 @@ using namespace vs;
 extern "C" {
 
 int vs_merge(int device, int metric, const float* cand_scores, const int32_t* cand_ids, int G,
-             int B, int k, float* out_scores, int32_t* out_ids, void* stream_) {
+             int B, int k, int64_t group_stride, float* out_scores, int32_t* out_ids,
+             void* stream_) {
   VS_REQUIRE(G >= 1 && B >= 0 && k >= 0, "G >= 1, B >= 0, k >= 0 required");
   VS_REQUIRE(metric >= 0 && metric <= 2, "bad metric");
   if (B == 0 || k == 0) return VS_OK;
   VS_REQUIRE(cand_scores && cand_ids && out_scores && out_ids, "NULL pointer");
+  if (group_stride == 0) group_stride = (int64_t)B * k;
+  VS_REQUIRE(group_stride >= (int64_t)B * k, "group_stride must be >= B*k");
   cudaStream_t stream = (cudaStream_t)stream_;
   VS_CUDA(cudaSetDevice(device));
-  // candidates arrive as (G, B, k) scores in reference convention (euclidean: distances);
-  // regroup them per query as keys (B, G*k) for the merge kernel.
-  float* tk = nullptr;
-  int32_t* ti = nullptr;
-  const size_t total = (size_t)G * B * k;
-  VS_CUDA(cudaMallocAsync((void**)&tk, total * 4, stream));
-  VS_CUDA(cudaMallocAsync((void**)&ti, total * 4, stream));
-  int rc = launch_regroup(cand_scores, cand_ids, G, B, k, metric == VS_METRIC_EUCLIDEAN, tk, ti, stream);
-  if (!rc) rc = launch_merge(tk, ti, (int64_t)G * k, B, k, nullptr, metric == VS_METRIC_EUCLIDEAN,
-                             out_scores, out_ids, k, stream);
-  cudaFreeAsync(tk, stream);
-  cudaFreeAsync(ti, stream);
-  return rc;
+  // candidates arrive as G groups of (B, k) scores in reference convention (euclidean:
+  // distances); the kernel reads them in place.
+  MergeParams p = {};
+  p.ck = cand_scores; p.ci = cand_ids;
+  p.per_query = (int64_t)G * k; p.chunk = k; p.chunk_stride = group_stride; p.query_stride = k;
+  p.k = k; p.tau = nullptr;
+  p.negate_in = p.negate_out = metric == VS_METRIC_EUCLIDEAN ? 1 : 0;
+  p.id_map = nullptr;
+  p.out_s = out_scores; p.out_i = out_ids; p.out_stride = k;
+  return launch_merge(p, B, stream);
 }
 
 int vs_normalize_rows(int device, const float* x, int64_t n, int dim, float* out, void* stream_) {

@@ -399,7 +399,10 @@ static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, 
     p.nlists = (int)blocks * kScanWarps;
     *nlists_out = p.nlists;
     if (dry_run) return VS_OK;
-    kern<<<(unsigned)blocks, kScanWarps * 32, smem, stream>>>(p);
+    {
+      ProfScope prof(kProfScan, stream);
+      kern<<<(unsigned)blocks, kScanWarps * 32, smem, stream>>>(p);
+    }
     count_launch();
     VS_CHECK_LAUNCH();
     return VS_OK;
@@ -412,7 +415,10 @@ static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, 
   p.nlists = (int)blocks * kScanWarps;
   *nlists_out = p.nlists;
   if (dry_run) return VS_OK;
-  kern<<<(unsigned)blocks, (kScanWarps + 1) * 32, smem, stream>>>(p);
+  {
+    ProfScope prof(kProfScan, stream);
+    kern<<<(unsigned)blocks, (kScanWarps + 1) * 32, smem, stream>>>(p);
+  }
   count_launch();
   VS_CHECK_LAUNCH();
   return VS_OK;

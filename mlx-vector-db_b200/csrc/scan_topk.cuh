@@ -41,13 +41,29 @@ int launch_prep_queries(const float* q, int B, int dim, int metric, int ldq, boo
                         float scale, float* out, float* qnorm_out, uint32_t* tau,
                         cudaStream_t stream);
 
-// K4
 // K4: per query, select the best `k` of `per_query` candidates (id < 0 = empty slot) into
 // out[b*out_stride ..]; slots [k, out_stride) are filled with id -1 / score 0.
-// `tau` (nullable) = encoded lower bound on the k-th best key, used as a pre-filter.
+struct MergeParams {
+  const float* ck;         // candidate scores / keys
+  const int32_t* ci;       // candidate ids (local row numbers), < 0 = empty
+  int64_t per_query;       // candidates per query
+  int64_t chunk;           // candidates per contiguous chunk
+  int64_t chunk_stride;    // elements between chunks of the same query
+  int64_t query_stride;    // elements between queries inside a chunk
+  int k;
+  const uint32_t* tau;     // nullable: encoded lower bound on the k-th best key (pre-filter)
+  int negate_in;           // candidates are distances: key = -score
+  int negate_out;          // write -key (euclidean distance)
+  const int32_t* id_map;   // nullable: local row -> global id (row-sharded stores)
+  float* out_s;
+  int32_t* out_i;
+  int64_t out_stride;
+};
+int launch_merge(const MergeParams& p, int B, cudaStream_t stream);
+// scan-list layout: candidates of query b contiguous at b * per_query
 int launch_merge(const float* cand_key, const int32_t* cand_id, int64_t per_query, int B, int k,
                  const uint32_t* tau, int negate_scores, float* out_scores, int32_t* out_ids,
-                 int64_t out_stride, cudaStream_t stream);
+                 int64_t out_stride, cudaStream_t stream, const int32_t* id_map = nullptr);
 
 // K5
 int launch_rescore(const float* rows, int ld, int dim, const float* norms, int metric,

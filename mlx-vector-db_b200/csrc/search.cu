@@ -47,7 +47,7 @@ static bool default_tma() {
 // out_*[b * out_stride ..], kk live entries each.
 static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool bf16,
                      bool use_tma, const uint32_t* row_mask, float* out_scores, int32_t* out_ids,
-                     int64_t out_stride, cudaStream_t stream) {
+                     int64_t out_stride, bool map_ids, cudaStream_t stream) {
   const int ldq = bf16 ? s->ld16 : s->ld;
   int qb_max = 8;
   while (qb_max > 1 && (size_t)kScanWarps * qb_max * kk * 8 > 64 * 1024) qb_max >>= 1;
@@ -99,7 +99,7 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
     if (int rc = launch_scan(p, qb, l2, bf16, use_tma, s->num_sms, &nl, nullptr, false, stream)) return rc;
     if (int rc = launch_merge(part_key, part_id, (int64_t)nl * kk, nb, kk, tau + b0, l2 ? 1 : 0,
                               out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride,
-                              out_stride, stream))
+                              out_stride, stream, map_ids ? s->id_map() : nullptr))
       return rc;
   }
   return VS_OK;
@@ -120,7 +120,7 @@ static int rescore_path(vs_store* s, const float* q, int B, const int32_t* cand,
                               s->metric, qprep, s->ld, B, cand, kc, keys, stream))
     return rc;
   return launch_merge(keys, cand, kc, B, kk, nullptr, s->metric == VS_METRIC_EUCLIDEAN ? 1 : 0,
-                      out_scores, out_ids, out_stride, stream);
+                      out_scores, out_ids, out_stride, stream, s->id_map());
 }
 
 }  // namespace vs
@@ -159,7 +159,7 @@ int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32
   }
   switch (mode) {
     case VS_SEARCH_SCAN_FP32:
-      return scan_path(s, n, q, B, kk, false, use_tma, row_mask, out_scores, out_ids, k, stream);
+      return scan_path(s, n, q, B, kk, false, use_tma, row_mask, out_scores, out_ids, k, true, stream);
     case VS_SEARCH_SCAN_BF16: {
       if (!s->shadow) { set_error("store was created without a bf16 shadow copy"); return VS_ERR_STATE; }
       // over-fetch, then exact fp32 rescoring of the candidates (K5)
@@ -171,7 +171,7 @@ int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32
       ws.want(&cs, (size_t)B * kc);
       ws.want(&ci, (size_t)B * kc);
       if (int rc = ws.alloc(stream)) return rc;
-      if (int rc = scan_path(s, n, q, B, kc, true, use_tma, row_mask, cs, ci, kc, stream)) return rc;
+      if (int rc = scan_path(s, n, q, B, kc, true, use_tma, row_mask, cs, ci, kc, false, stream)) return rc;
       return rescore_path(s, q, B, ci, kc, kk, out_scores, out_ids, k, stream);
     }
     case VS_SEARCH_GEMM:

@@ -21,6 +21,26 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return e == cudaErrorMemoryAllocation ? VS_ERR_OOM : VS_ERR_CUDA;
 }
 
+// --------------------------------------------------------------- profiling
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct ProfPair { cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof[kProfKinds];
+
+ProfScope::ProfScope(int kind, cudaStream_t stream) : stream_(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfPair p;
+  if (cudaEventCreate(&p.a) != cudaSuccess) return;
+  if (cudaEventCreate(&p.b) != cudaSuccess) { cudaEventDestroy(p.a); return; }
+  cudaEventRecord(p.a, stream);
+  stop_ = p.b;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  g_prof[kind].push_back(p);
+}
+ProfScope::~ProfScope() {
+  if (stop_) cudaEventRecord(stop_, stream_);
+}
+
 // --------------------------------------------------- driver API via cudart
 // libcuda is not linked: the library must load (and export its symbols) on a box without a
 // driver; the entry points are resolved at first use through the runtime.
@@ -181,7 +201,7 @@ __global__ void __launch_bounds__(256)
 append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
                    int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
                    float* __restrict__ sqnorms, __nv_bfloat16* __restrict__ shadow, int ld16,
-                   int normalize_shadow) {
+                   int normalize_shadow, int32_t* __restrict__ gids, int64_t gid0) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -197,7 +217,11 @@ append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restr
     }
     const float tot = warp_sum(acc);
     const float nrm = fmaxf(sqrtf(tot), 1e-8f);
-    if (lane == 0) { norms[n0 + r] = nrm; sqnorms[n0 + r] = tot; }
+    if (lane == 0) {
+      norms[n0 + r] = nrm;
+      sqnorms[n0 + r] = tot;
+      if (gids != nullptr) gids[n0 + r] = (int32_t)(gid0 + r);
+    }
     if (shadow != nullptr) {
       __nv_bfloat16* sh = shadow + (n0 + r) * (int64_t)ld16;
       for (int c = lane; c < ld16; c += 32) {
@@ -219,6 +243,33 @@ extern "C" {
 const char* vs_last_error(void) { return t_error.c_str(); }
 const char* vs_version(void) { return "b200vs 0.1 (sm_100a)"; }
 int64_t vs_launch_count(void) { return g_launches.load(); }
+
+int vs_profile(int enable) {
+  g_prof_on.store(enable ? 1 : 0);
+  return VS_OK;
+}
+
+int vs_profile_read(int kind, double* total_ms, int64_t* launches) {
+  VS_REQUIRE(kind >= 0 && kind < kProfKinds, "unknown profile kind");
+  VS_REQUIRE(total_ms && launches, "NULL pointer");
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  double sum = 0.0;
+  int64_t n = 0;
+  for (auto& p : g_prof[kind]) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      sum += ms;
+      ++n;
+    }
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  cudaGetLastError();
+  g_prof[kind].clear();
+  *total_ms = sum;
+  *launches = n;
+  return VS_OK;
+}
 
 int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_store** out) {
   VS_REQUIRE(out != nullptr, "out is NULL");
@@ -256,6 +307,7 @@ int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_
   if (!rc) rc = s->norms.init(device, (size_t)max_rows * 4);
   if (!rc) rc = s->sqnorms.init(device, (size_t)max_rows * 4);
   if (!rc && shadow) rc = s->shadow_rows.init(device, (size_t)max_rows * s->ld16 * 2);
+  if (!rc) rc = s->gids.init(device, (size_t)max_rows * 4);
   if (rc) { vs_destroy(s); return rc; }
   // keep stream-ordered workspace memory cached in the pool between searches
   cudaMemPool_t pool;
@@ -282,6 +334,7 @@ int vs_destroy(vs_store* s) {
   s->norms.destroy();
   s->sqnorms.destroy();
   s->shadow_rows.destroy();
+  s->gids.destroy();
   if (s->append_done) cudaEventDestroy(s->append_done);
   if (s->host_stream) cudaStreamDestroy(s->host_stream);
   if (s->pinned_in) cudaFreeHost(s->pinned_in);
@@ -297,17 +350,24 @@ int64_t vs_fallback_count(const vs_store* s) { return s ? s->fallbacks.load() : 
 int64_t vs_memory_bytes(const vs_store* s) {
   if (!s) return 0;
   return (int64_t)(s->rows.mapped() + s->norms.mapped() + s->sqnorms.mapped() +
-                   s->shadow_rows.mapped());
+                   s->shadow_rows.mapped() + s->gids.mapped());
 }
 
 int vs_reset(vs_store* s) {
   VS_REQUIRE(s != nullptr, "store is NULL");
   std::lock_guard<std::mutex> g(s->mu);
   s->count.store(0, std::memory_order_release);
+  s->mapped = false;
   return VS_OK;
 }
 
-int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device, void* stream_) {
+__global__ void iota_kernel(int32_t* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)i;
+}
+
+static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_device,
+                       int64_t first_global_id, void* stream_) {
   VS_REQUIRE(s != nullptr, "store is NULL");
   VS_REQUIRE(m >= 0, "m must be >= 0");
   if (m == 0) return VS_OK;
@@ -323,6 +383,21 @@ int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device, voi
   if (int rc = s->sqnorms.ensure((size_t)n1 * 4, stream)) return rc;
   if (s->shadow)
     if (int rc = s->shadow_rows.ensure((size_t)n1 * s->ld16 * 2, stream)) return rc;
+  const bool with_ids = first_global_id >= 0;
+  if (s->mapped && !with_ids) {
+    set_error("store maps local rows to global ids: append with vs_append_ids");
+    return VS_ERR_STATE;
+  }
+  if (with_ids) {
+    VS_REQUIRE(first_global_id + m <= (int64_t)0x7fffffff, "global ids must be < 2^31");
+    if (int rc = s->gids.ensure((size_t)n1 * 4, stream)) return rc;
+    if (!s->mapped && n0 > 0) {   // rows appended so far keep their identity ids
+      iota_kernel<<<(unsigned)std::min<int64_t>((n0 + 255) / 256, 1184), 256, 0, stream>>>(
+          (int32_t*)s->gids.ptr(), n0);
+      count_launch();
+      VS_CHECK_LAUNCH();
+    }
+  }
 
   float* master = (float*)s->rows.ptr();
   const int64_t piece = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)s->dim * 4));
@@ -351,7 +426,8 @@ int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device, voi
     append_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
         ksrc, ksrc_ld, master, s->ld, s->dim, n0 + off, mm, (float*)s->norms.ptr(),
         (float*)s->sqnorms.ptr(), s->shadow ? (__nv_bfloat16*)s->shadow_rows.ptr() : nullptr,
-        s->ld16, s->metric == VS_METRIC_COSINE ? 1 : 0);
+        s->ld16, s->metric == VS_METRIC_COSINE ? 1 : 0,
+        with_ids ? (int32_t*)s->gids.ptr() : nullptr, with_ids ? first_global_id + off : 0);
     count_launch();
     VS_CHECK_LAUNCH();
     if (staging) VS_CUDA(cudaFreeAsync(staging, stream));
@@ -360,8 +436,19 @@ int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device, voi
   // searches on other streams wait for this event before reading the new rows
   VS_CUDA(cudaEventRecord(s->append_done, stream));
   s->append_stream = stream;
+  if (with_ids) s->mapped = true;
   s->count.store(n1, std::memory_order_release);
   return VS_OK;
+}
+
+int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device, void* stream) {
+  return append_impl(s, rows, m, rows_on_device, -1, stream);
+}
+
+int vs_append_ids(vs_store* s, const float* rows, int64_t m, int rows_on_device,
+                  int64_t first_global_id, void* stream) {
+  VS_REQUIRE(first_global_id >= 0, "first_global_id must be >= 0");
+  return append_impl(s, rows, m, rows_on_device, first_global_id, stream);
 }
 
 int vs_read_rows(vs_store* s, int64_t first, int64_t m, float* out, int out_on_device,

@@ -321,3 +321,52 @@ class OracleVectorStore:
                     self._metadata = [json.loads(line) for line in f]
         except Exception:
             self._vectors, self._metadata, self._vector_count = None, [], 0
+
+
+# --------------------------------------------------------------------------- #
+# timed variant for bench.py's CPU baseline / reference arm
+# --------------------------------------------------------------------------- #
+def batch_similarity_search_timed(queries, db, k: int = 10, threads: int = 1):
+    """`batch_similarity_search` (performance/mlx_optimized.py:217-248) with its three phases
+    timed separately and spread over `threads` host threads where NumPy itself is serial:
+    (1) normalise queries and the WHOLE database (:69-83, done on every call by the
+    reference), (2) one fp32 GEMM (:86, BLAS threads), (3) per-row full stable argsort of the
+    negated scores + gather (:235-244).  Same arithmetic and tie rule as the untimed function.
+    Returns (ids, scores, {"normalize_s", "matmul_s", "argsort_s"})."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    q = to_f32(queries)
+    v = to_f32(db)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    B, n = q.shape[0], v.shape[0]
+    kk = max(0, min(int(k), n))
+    threads = max(1, int(threads))
+    t0 = time.perf_counter()
+    qn = q / np.maximum(_row_norms(q), EPS)
+    vn = np.empty_like(v)
+
+    def _norm_block(lo_hi):
+        lo, hi = lo_hi
+        blk = v[lo:hi]
+        np.divide(blk, np.maximum(_row_norms(blk), EPS), out=vn[lo:hi])
+
+    step = max(1, (n + threads - 1) // threads)
+    blocks = [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(_norm_block, blocks))
+        t1 = time.perf_counter()
+        s = qn @ vn.T
+        t2 = time.perf_counter()
+        ids = np.empty((B, kk), np.int32)
+        sc = np.empty((B, kk), np.float32)
+
+        def _sort_row(b):
+            order = np.argsort(-s[b], kind="stable")[:kk]
+            ids[b] = order
+            sc[b] = s[b][order]
+
+        list(ex.map(_sort_row, range(B)))
+        t3 = time.perf_counter()
+    return ids, sc, {"normalize_s": t1 - t0, "matmul_s": t2 - t1, "argsort_s": t3 - t2}

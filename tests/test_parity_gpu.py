@@ -233,7 +233,7 @@ def test_merge_of_shard_results_equals_global(make_store):
         os_ = torch.empty((b, k), dtype=torch.float32, device="cuda")
         oi = torch.empty((b, k), dtype=torch.int32, device="cuda")
         _cabi.check(_cabi.lib().vs_merge(0, _cabi.METRICS[metric], C.c_void_p(dcs.data_ptr()),
-                                         C.c_void_p(dci.data_ptr()), G, b, k,
+                                         C.c_void_p(dci.data_ptr()), G, b, k, 0,
                                          C.c_void_p(os_.data_ptr()), C.c_void_p(oi.data_ptr()),
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()

@@ -4,8 +4,8 @@
 
 namespace vs {
 
-constexpr int kMergeCap = 2048;     // candidates sorted in shared memory
-constexpr int kMergeThreads = 256;
+constexpr int kMergeCap = 4096;     // candidates sorted in shared memory
+constexpr int kMergeThreads = 512;
 
 // One CTA per query.  Candidate i of query b lives at
 //   (i / chunk) * chunk_stride + b * query_stride + (i % chunk)
@@ -30,19 +30,84 @@ __device__ __forceinline__ bool cand_load(const MergeParams& p, int b, int64_t i
   return true;
 }
 
+// bitonic sort of sk[0..n2) (and si when WITH_ID) in shared memory, best first
+template <bool WITH_ID>
+__device__ __forceinline__ void smem_bitonic(float* sk, int* si, int n2, int tid) {
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n2; i += kMergeThreads) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool fwd = (i & size) == 0;
+          const float ka = sk[i], kb = sk[j];
+          if (WITH_ID) {
+            const int ia = si[i], ib = si[j];
+            const bool swap = fwd ? better(kb, ib, ka, ia) : better(ka, ia, kb, ib);
+            if (swap) { sk[i] = kb; si[i] = ib; sk[j] = ka; si[j] = ia; }
+          } else {
+            if (fwd ? (kb > ka) : (ka > kb)) { sk[i] = kb; sk[j] = ka; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr int kRankCap = 1024;   // up to this many items are ordered by counting ranks
+
 __global__ void __launch_bounds__(kMergeThreads)
 merge_topk_kernel(const MergeParams p) {
   __shared__ float sk[kMergeCap];
   __shared__ int si[kMergeCap];
   __shared__ int cnt;
+  __shared__ float thr_sh;
   __shared__ float red_k[kMergeThreads / 32];
   __shared__ int red_i[kMergeThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int k = p.k;
   float* os = p.out_s + (int64_t)b * p.out_stride;
   int32_t* oi = p.out_i + (int64_t)b * p.out_stride;
-  const float thr = p.tau ? dec_key(p.tau[b]) : VS_NEG_INF;
-  if (tid == 0) cnt = 0;
+  float thr = p.tau ? dec_key(p.tau[b]) : VS_NEG_INF;
+  if (tid == 0) { cnt = 0; thr_sh = VS_NEG_INF; }
+  // Head-sample pre-filter for sorted lists: with L lists and pos = ceil(k / L), every list
+  // whose pos-th entry is >= t holds at least pos candidates >= t, so t = the
+  // ceil(k / pos)-th largest pos-th entry is a lower bound on the k-th best key.
+  if (p.list_len > 0 && p.per_query > 2 * (int64_t)k) {
+    const int64_t L = p.per_query / p.list_len;
+    int pos = (int)((k + L - 1) / L);
+    if (pos < 1) pos = 1;
+    const int need = (k + pos - 1) / pos;
+    if (L >= 2 && L <= kMergeCap && pos <= p.list_len && need <= L) {
+      int n2 = 1;
+      while (n2 < L) n2 <<= 1;
+      for (int i = tid; i < n2; i += kMergeThreads) {
+        float key = VS_NEG_INF;
+        if (i < L) {
+          const int64_t a = cand_addr(p, b, (int64_t)i * p.list_len + pos - 1);
+          if (p.ci[a] >= 0) key = p.negate_in ? -p.ck[a] : p.ck[a];
+        }
+        sk[i] = key;
+      }
+      __syncthreads();
+      if (L <= kRankCap) {
+        for (int i = tid; i < (int)L; i += kMergeThreads) {
+          const float mine = sk[i];
+          int r = 0;
+          for (int j = 0; j < (int)L; ++j) {
+            const float o = sk[j];
+            r += (o > mine) || (o == mine && j < i);
+          }
+          if (r == need - 1) thr_sh = mine;
+        }
+      } else {
+        smem_bitonic<false>(sk, si, n2, tid);
+        if (tid == 0) thr_sh = sk[need - 1];
+      }
+      __syncthreads();
+      thr = fmaxf(thr, thr_sh);
+    }
+  }
   __syncthreads();
   for (int64_t i = tid; i < p.per_query; i += kMergeThreads) {
     float key; int id;
@@ -54,26 +119,22 @@ merge_topk_kernel(const MergeParams p) {
   __syncthreads();
   const int n = cnt;
   int written = 0;
-  if (n <= kMergeCap) {
+  if (n <= kRankCap) {
+    // order by counting: rank = number of better survivors; the first k ranks are written
+    for (int i = tid; i < n; i += kMergeThreads) {
+      const float mk = sk[i];
+      const int mi = si[i];
+      int r = 0;
+      for (int j = 0; j < n; ++j) r += better(sk[j], si[j], mk, mi);
+      if (r < k) { os[r] = p.negate_out ? -mk : mk; oi[r] = mi; }
+    }
+    written = n < k ? n : k;
+  } else if (n <= kMergeCap) {
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
     for (int i = n + tid; i < n2; i += kMergeThreads) { sk[i] = VS_NEG_INF; si[i] = VS_ID_SENTINEL; }
     __syncthreads();
-    for (int size = 2; size <= n2; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = tid; i < n2; i += kMergeThreads) {
-          const int j = i ^ stride;
-          if (j > i) {
-            const bool fwd = (i & size) == 0;
-            const float ka = sk[i], kb = sk[j];
-            const int ia = si[i], ib = si[j];
-            const bool swap = fwd ? better(kb, ib, ka, ia) : better(ka, ia, kb, ib);
-            if (swap) { sk[i] = kb; si[i] = ib; sk[j] = ka; si[j] = ia; }
-          }
-        }
-        __syncthreads();
-      }
-    }
+    smem_bitonic<true>(sk, si, n2, tid);
     written = n < k ? n : k;
     for (int i = tid; i < written; i += kMergeThreads) {
       os[i] = p.negate_out ? -sk[i] : sk[i];
@@ -123,8 +184,9 @@ int launch_merge(const MergeParams& p, int B, cudaStream_t stream) {
 
 int launch_merge(const float* cand_key, const int32_t* cand_id, int64_t per_query, int B, int k,
                  const uint32_t* tau, int negate_scores, float* out_scores, int32_t* out_ids,
-                 int64_t out_stride, cudaStream_t stream, const int32_t* id_map) {
+                 int64_t out_stride, cudaStream_t stream, const int32_t* id_map, int list_len) {
   MergeParams p = {};
+  p.list_len = list_len;
   p.ck = cand_key; p.ci = cand_id;
   p.per_query = per_query; p.chunk = per_query > 0 ? per_query : 1; p.chunk_stride = 0;
   p.query_stride = per_query;
@@ -242,6 +304,7 @@ int vs_merge(int device, int metric, const float* cand_scores, const int32_t* ca
   MergeParams p = {};
   p.ck = cand_scores; p.ci = cand_ids;
   p.per_query = (int64_t)G * k; p.chunk = k; p.chunk_stride = group_stride; p.query_stride = k;
+  p.list_len = k;
   p.k = k; p.tau = nullptr;
   p.negate_in = p.negate_out = metric == VS_METRIC_EUCLIDEAN ? 1 : 0;
   p.id_map = nullptr;

@@ -7,6 +7,7 @@
 // threshold; a grid-wide threshold (atomicMax on an order-preserving encoding) prunes rows
 // that can no longer enter the global top-k.  Row r is skipped iff key < tau, so ties at the
 // threshold survive and the final (key desc, id asc) order is deterministic.
+#include <cstdlib>
 #include "scan_topk.cuh"
 
 namespace vs {
@@ -147,18 +148,18 @@ struct Acc<L2, true> {
 // Shared-memory carve-up common to both variants.
 struct ScanSmem {
   float4* q;     // (QB, ldq/4)
-  float* lk;     // (kScanWarps, QB, k)
+  float* lk;     // (warps, QB, k)
   int* li;
 };
-__device__ __forceinline__ ScanSmem carve(unsigned char* smem, int qb, int ldq, int k) {
+__device__ __forceinline__ ScanSmem carve(unsigned char* smem, int qb, int ldq, int k, int warps) {
   ScanSmem s;
   s.q = reinterpret_cast<float4*>(smem);
   s.lk = reinterpret_cast<float*>(smem + (size_t)qb * ldq * 4);
-  s.li = reinterpret_cast<int*>(s.lk + (size_t)kScanWarps * qb * k);
+  s.li = reinterpret_cast<int*>(s.lk + (size_t)warps * qb * k);
   return s;
 }
-static size_t scan_fixed_smem(int qb, int ldq, int k) {
-  size_t b = (size_t)qb * ldq * 4 + (size_t)kScanWarps * qb * k * 8;
+static size_t scan_fixed_smem(int qb, int ldq, int k, int warps) {
+  size_t b = (size_t)qb * ldq * 4 + (size_t)warps * qb * k * 8;
   return (size_t)round_up((int64_t)b, 128);
 }
 
@@ -170,7 +171,7 @@ __device__ __forceinline__ void scan_prologue(const ScanParams& p, const ScanSme
     const int b = i / qv;
     s.q[i] = b < p.nb ? gq[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int i = threadIdx.x; i < kScanWarps * QB * p.k; i += nthreads) {
+  for (int i = threadIdx.x; i < p.warps * QB * p.k; i += nthreads) {
     s.lk[i] = VS_NEG_INF;
     s.li[i] = VS_ID_SENTINEL;
   }
@@ -191,7 +192,6 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams& p, const ScanSme
   if (p.epilogue == VS_METRIC_COSINE) key = total / nrm;
   else if (p.epilogue == VS_METRIC_EUCLIDEAN) key = -sqrtf(total);
   else key = total;
-  my_tau = fmaxf(my_tau, dec_key(__ldcg(p.tau + my_b)));
   const bool pass = rep && row_ok && (my_b < p.nb) && (key >= my_tau);
   unsigned m = __ballot_sync(0xffffffffu, pass);
   while (m) {
@@ -208,16 +208,35 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams& p, const ScanSme
   }
 }
 
+// End of the scan: the consumer warps of a CTA merge their sorted k-lists into ONE sorted
+// k-list per query (a `warps`-way merge: lane l walks list l, a shuffle butterfly picks the
+// best head k times), so the grid leaves gridDim.x lists per query behind instead of
+// gridDim.x * warps.
 template <int QB>
-__device__ __forceinline__ void scan_write_lists(const ScanParams& p, const ScanSmem& s, int lane,
-                                                 int warp, int64_t list) {
-  for (int b = 0; b < p.nb; ++b) {
-    const size_t src = ((size_t)warp * QB + b) * p.k;
-    const size_t dst = ((size_t)b * p.nlists + list) * p.k;
-    for (int e = lane; e < p.k; e += 32) {
-      const int id = s.li[src + e];
-      p.part_key[dst + e] = s.lk[src + e];
-      p.part_id[dst + e] = id == VS_ID_SENTINEL ? -1 : id;
+__device__ __forceinline__ void scan_block_merge(const ScanParams& p, const ScanSmem& s, int lane,
+                                                 int warp) {
+  asm volatile("bar.sync 1, %0;" ::"r"(p.warps * 32) : "memory");   // consumer warps only
+  for (int b = warp; b < p.nb; b += p.warps) {
+    const bool has = lane < p.warps;
+    const size_t src = ((size_t)(has ? lane : 0) * QB + b) * p.k;
+    const size_t dst = ((size_t)b * p.nlists + blockIdx.x) * p.k;
+    int head = 0;
+    for (int j = 0; j < p.k; ++j) {
+      float bk = VS_NEG_INF;
+      int bi = VS_ID_SENTINEL, bl = lane;
+      if (has && head < p.k) { bk = s.lk[src + head]; bi = s.li[src + head]; }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        const int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+        if (better(ok, oi, bk, bi)) { bk = ok; bi = oi; bl = ol; }
+      }
+      if (lane == bl && bi != VS_ID_SENTINEL) ++head;
+      if (lane == 0) {
+        p.part_key[dst + j] = bk;
+        p.part_id[dst + j] = bi == VS_ID_SENTINEL ? -1 : bi;
+      }
     }
   }
 }
@@ -228,23 +247,24 @@ __device__ __forceinline__ bool mask_bit(const uint32_t* mask, int64_t row) {
 
 // ------------------------------------------------------------ LDG variant
 template <int QB, int R, bool L2, bool BF16>
-__global__ void __launch_bounds__(kScanWarps * 32)
+__global__ void __launch_bounds__(kMaxScanWarps * 32)
 scan_topk_ldg_kernel(const ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   using A = Acc<L2, BF16>;
   constexpr int V = QB * R;
   constexpr int SH = 5 - Log2<V>::value;
-  const ScanSmem s = carve(smem, QB, p.ldq, p.k);
+  const ScanSmem s = carve(smem, QB, p.ldq, p.k, p.warps);
   scan_prologue<QB>(p, s, blockDim.x);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t gw = (int64_t)blockIdx.x * kScanWarps + warp;
-  const int64_t nw = (int64_t)gridDim.x * kScanWarps;
+  const int64_t gw = (int64_t)blockIdx.x * p.warps + warp;
+  const int64_t nw = (int64_t)gridDim.x * p.warps;
   const int nvec = p.vec_per_row;
   const int qstride = p.ldq >> 2;           // float4 per prepared query
   const int plane = qstride >> 1;           // bf16: second 4-float plane
   const int my_r = (lane >> SH) / QB;
+  const int my_b = (lane >> SH) % QB;
   float my_tau = VS_NEG_INF;
 
   for (int64_t row0 = gw * R; row0 < p.n; row0 += nw * R) {
@@ -253,6 +273,7 @@ scan_topk_ldg_kernel(const ScanParams p) {
     const bool row_ok = my_row < p.n && mask_bit(p.row_mask, my_row);
     float nrm = 1.f;
     if (p.epilogue == VS_METRIC_COSINE && p.norms != nullptr && my_row < p.n) nrm = __ldg(p.norms + my_row);
+    const uint32_t gtau = __ldcg(p.tau + my_b);
 
     float acc[V];
 #pragma unroll
@@ -275,35 +296,41 @@ scan_topk_ldg_kernel(const ScanParams p) {
           acc[r * QB + b] = A::run(acc[r * QB + b], x[r], s.q + b * qstride, c, plane);
     }
     reduce_scatter<V>(acc, lane);
+    my_tau = fmaxf(my_tau, dec_key(gtau));
     scan_epilogue<QB, R>(p, s, acc[0], row0, nrm, row_ok, lane, warp, my_tau);
   }
   __syncwarp();
-  scan_write_lists<QB>(p, s, lane, warp, gw);
+  scan_block_merge<QB>(p, s, lane, warp);
 }
 
 // ------------------------------------------------------------ TMA variant
-// Warp kScanWarps is the producer; warps 0..7 consume.  Ring of p.stages tiles of
-// p.tile_rows rows; full[s] (count 1 + tx bytes) / empty[s] (count 8) mbarriers.
+// Warp p.warps is the producer; warps 0..p.warps-1 consume.  Ring of p.stages tiles of
+// p.tile_rows rows (+ their clamped norms for fp32 cosine, a second bulk copy on the same
+// barrier); full[s] (count 1 + tx bytes) / empty[s] (count p.warps) mbarriers.
 template <int QB, int R, bool L2, bool BF16>
-__global__ void __launch_bounds__((kScanWarps + 1) * 32, 1)
+__global__ void __launch_bounds__((kMaxTmaWarps + 1) * 32, 1)
 scan_topk_tma_kernel(const ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   using A = Acc<L2, BF16>;
   constexpr int V = QB * R;
   constexpr int SH = 5 - Log2<V>::value;
-  const ScanSmem s = carve(smem, QB, p.ldq, p.k);
-  const size_t fixed = ((size_t)QB * p.ldq * 4 + (size_t)kScanWarps * QB * p.k * 8 + 127) / 128 * 128;
+  const int nwarps = p.warps;
+  const ScanSmem s = carve(smem, QB, p.ldq, p.k, nwarps);
+  const size_t fixed = ((size_t)QB * p.ldq * 4 + (size_t)nwarps * QB * p.k * 8 + 127) / 128 * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + fixed);       // full[stages], empty[stages]
   unsigned char* tiles = smem + fixed + 128;                        // 16 barriers max
   const int row_bytes = p.vec_per_row * 16;
   const uint32_t tile_bytes = (uint32_t)p.tile_rows * row_bytes;
+  const bool stage_norms = p.epilogue == VS_METRIC_COSINE && p.norms != nullptr;
+  const uint32_t norm_bytes = stage_norms ? (uint32_t)p.tile_rows * 4 : 0;   // multiple of 16
+  const uint32_t stage_bytes = tile_bytes + norm_bytes;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   scan_prologue<QB>(p, s, blockDim.x);
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(smem_u32(bars + i), 1);
-      mbar_init(smem_u32(bars + p.stages + i), kScanWarps);
+      mbar_init(smem_u32(bars + p.stages + i), nwarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -311,7 +338,7 @@ scan_topk_tma_kernel(const ScanParams p) {
 
   const int64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
 
-  if (warp == kScanWarps) {
+  if (warp == nwarps) {
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
@@ -320,10 +347,14 @@ scan_topk_tma_kernel(const ScanParams p) {
         const int64_t first = t * p.tile_rows;
         const int64_t rows = p.n - first < p.tile_rows ? p.n - first : p.tile_rows;
         const uint32_t bytes = (uint32_t)(rows * row_bytes);
+        // norms: whole 16 B granules (the arena keeps slack past row n, see store.cu)
+        const uint32_t nbytes = stage_norms ? (uint32_t)((rows * 4 + 15) & ~15) : 0;
         const uint32_t full = smem_u32(bars + st);
-        mbar_expect_tx(full, bytes);
-        tma_load_1d(smem_u32(tiles + (size_t)st * tile_bytes),
-                    reinterpret_cast<const unsigned char*>(p.db) + first * row_bytes, bytes, full);
+        unsigned char* dst = tiles + (size_t)st * stage_bytes;
+        mbar_expect_tx(full, bytes + nbytes);
+        tma_load_1d(smem_u32(dst), reinterpret_cast<const unsigned char*>(p.db) + first * row_bytes,
+                    bytes, full);
+        if (stage_norms) tma_load_1d(smem_u32(dst + tile_bytes), p.norms + first, nbytes, full);
         if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
     }
@@ -334,13 +365,19 @@ scan_topk_tma_kernel(const ScanParams p) {
   const int qstride = p.ldq >> 2;
   const int plane = qstride >> 1;
   const int my_r = (lane >> SH) / QB;
-  const int rows_per_warp = p.tile_rows / kScanWarps;   // multiple of R
+  const int my_b = (lane >> SH) % QB;
+  const int rows_per_warp = p.tile_rows / nwarps;   // multiple of R
   float my_tau = VS_NEG_INF;
   int st = 0;
   uint32_t ph = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // the grid-wide threshold is refreshed once per tile; its L2 latency overlaps the wait
+    const uint32_t gtau = __ldcg(p.tau + my_b);
     mbar_wait(smem_u32(bars + st), ph);
-    const typename A::Vec* tile = reinterpret_cast<const typename A::Vec*>(tiles + (size_t)st * tile_bytes);
+    my_tau = fmaxf(my_tau, dec_key(gtau));
+    const unsigned char* stage = tiles + (size_t)st * stage_bytes;
+    const typename A::Vec* tile = reinterpret_cast<const typename A::Vec*>(stage);
+    const float* tnorm = reinterpret_cast<const float*>(stage + tile_bytes);
     for (int rr = 0; rr < rows_per_warp; rr += R) {
       const int lrow0 = warp * rows_per_warp + rr;            // row within the tile
       const int64_t row0 = t * p.tile_rows + lrow0;
@@ -348,7 +385,7 @@ scan_topk_tma_kernel(const ScanParams p) {
       const int64_t my_row = row0 + my_r;
       const bool row_ok = my_row < p.n && mask_bit(p.row_mask, my_row);
       float nrm = 1.f;
-      if (p.epilogue == VS_METRIC_COSINE && p.norms != nullptr && my_row < p.n) nrm = __ldg(p.norms + my_row);
+      if (stage_norms && my_row < p.n) nrm = tnorm[lrow0 + my_r];
       float acc[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = 0.f;
@@ -375,49 +412,58 @@ scan_topk_tma_kernel(const ScanParams p) {
     if (++st == p.stages) { st = 0; ph ^= 1u; }
   }
   __syncwarp();
-  scan_write_lists<QB>(p, s, lane, warp, (int64_t)blockIdx.x * kScanWarps + warp);
+  scan_block_merge<QB>(p, s, lane, warp);
 }
 
 // ---------------------------------------------------------------- launcher
+// tuning knobs (diagnostic): B200VS_SCAN_WARPS, B200VS_SCAN_R, B200VS_SCAN_MAXWARPS
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+
 template <int QB, int R, bool L2, bool BF16>
 static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, bool dry_run,
                       cudaStream_t stream) {
-  const size_t fixed = scan_fixed_smem(QB, p.ldq, p.k);
+  const size_t fixed = scan_fixed_smem(QB, p.ldq, p.k, p.warps);
   if (!use_tma) {
     auto kern = scan_topk_ldg_kernel<QB, R, L2, BF16>;
     const size_t smem = fixed;
     if (smem > 48 * 1024)
       VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScanWarps * 32, smem));
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p.warps * 32, smem));
     if (per_sm < 1) { set_error("scan kernel does not fit on an SM (k or dim too large)"); return VS_ERR_INVALID; }
-    if (per_sm > 4) per_sm = 4;
+    const int max_warps = env_int("B200VS_SCAN_MAXWARPS", 32);
+    if (per_sm * p.warps > max_warps) per_sm = max_warps / p.warps > 0 ? max_warps / p.warps : 1;
     int64_t groups = (p.n + R - 1) / R;
-    int64_t blocks = (groups + kScanWarps - 1) / kScanWarps;
+    int64_t blocks = (groups + p.warps - 1) / p.warps;
     const int64_t cap = (int64_t)num_sms * per_sm;
     if (blocks > cap) blocks = cap;
-    p.nlists = (int)blocks * kScanWarps;
+    p.nlists = (int)blocks;
     *nlists_out = p.nlists;
     if (dry_run) return VS_OK;
     {
       ProfScope prof(kProfScan, stream);
-      kern<<<(unsigned)blocks, kScanWarps * 32, smem, stream>>>(p);
+      kern<<<(unsigned)blocks, p.warps * 32, smem, stream>>>(p);
     }
     count_launch();
     VS_CHECK_LAUNCH();
     return VS_OK;
   }
   auto kern = scan_topk_tma_kernel<QB, R, L2, BF16>;
-  const size_t smem = fixed + 128 + (size_t)p.stages * p.tile_rows * p.vec_per_row * 16;
+  const bool stage_norms = p.epilogue == VS_METRIC_COSINE && p.norms != nullptr;
+  const size_t smem = fixed + 128 +
+                      (size_t)p.stages * ((size_t)p.tile_rows * p.vec_per_row * 16 + (stage_norms ? p.tile_rows * 4 : 0));
   VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
   int64_t blocks = ntiles < num_sms ? ntiles : num_sms;
-  p.nlists = (int)blocks * kScanWarps;
+  p.nlists = (int)blocks;
   *nlists_out = p.nlists;
   if (dry_run) return VS_OK;
   {
     ProfScope prof(kProfScan, stream);
-    kern<<<(unsigned)blocks, (kScanWarps + 1) * 32, smem, stream>>>(p);
+    kern<<<(unsigned)blocks, (p.warps + 1) * 32, smem, stream>>>(p);
   }
   count_launch();
   VS_CHECK_LAUNCH();
@@ -432,6 +478,7 @@ static int launch_r(const ScanParams& p, int r, bool use_tma, int num_sms, int* 
     case 2: return launch_one<QB, 2, L2, BF16>(p, use_tma, num_sms, nl, dry, st);
     case 4: if constexpr (QB <= 4) return launch_one<QB, 4, L2, BF16>(p, use_tma, num_sms, nl, dry, st); break;
     case 8: if constexpr (QB <= 2) return launch_one<QB, 8, L2, BF16>(p, use_tma, num_sms, nl, dry, st); break;
+    case 16: if constexpr (QB == 1) return launch_one<QB, 16, L2, BF16>(p, use_tma, num_sms, nl, dry, st); break;
   }
   set_error("internal: unsupported rows-per-warp");
   return VS_ERR_INVALID;
@@ -453,21 +500,28 @@ static int launch_qb(const ScanParams& p, int qb, int r, bool use_tma, int num_s
 int launch_scan(const ScanParams& base, int qb, bool l2, bool bf16, bool use_tma, int num_sms,
                 int* nlists_out, size_t* part_elems_out, bool dry_run, cudaStream_t stream) {
   ScanParams p = base;
+  // consumer warps: 12 while the per-warp lists stay small, else 8
+  p.warps = scan_warps_for(qb, p.k);
+  const int ew = env_int("B200VS_SCAN_WARPS", 0);
+  if (ew > 0 && ew <= kMaxScanWarps && (size_t)ew * qb * p.k * 8 <= 64 * 1024) p.warps = ew;
   // rows in flight per warp: bounded by the V = QB*R <= 16 accumulators
-  int r = qb == 1 ? 8 : (qb == 2 ? 4 : (qb == 4 ? 4 : 2));
+  int r = 16 / qb;
+  const int er = env_int("B200VS_SCAN_R", 0);
+  if (er > 0 && er * qb <= 16 && (er & (er - 1)) == 0) r = er;
   const int row_bytes = p.vec_per_row * 16;
+  if (use_tma && p.warps > kMaxTmaWarps) p.warps = kMaxTmaWarps;
   if (use_tma) {
-    // tile = 8 warps x rows_per_warp rows, about 32 KB; at least 2 stages must fit
-    const size_t fixed = scan_fixed_smem(qb, p.ldq, p.k) + 128;
+    // tile = warps x rows_per_warp rows, about 32 KB; at least 2 stages must fit
+    const size_t fixed = scan_fixed_smem(qb, p.ldq, p.k, p.warps) + 128;
     const size_t budget = 200 * 1024 > fixed ? 200 * 1024 - fixed : 0;
     int rpw = 8;
-    while (rpw > 1 && (size_t)kScanWarps * rpw * row_bytes > 32 * 1024) rpw >>= 1;
+    while (rpw > 1 && (size_t)p.warps * rpw * row_bytes > 32 * 1024) rpw >>= 1;
     if (r > rpw) r = rpw;
-    const size_t tile = (size_t)kScanWarps * rpw * row_bytes;
+    const size_t tile = (size_t)p.warps * rpw * (row_bytes + 4);
     int stages = (int)(budget / tile);
     if (stages > 6) stages = 6;
     if (stages < 2) use_tma = false;   // rows too wide to stage: stream them directly
-    p.tile_rows = kScanWarps * rpw;
+    p.tile_rows = p.warps * rpw;
     p.stages = stages;
   }
   int rc;

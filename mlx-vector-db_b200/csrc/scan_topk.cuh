@@ -6,8 +6,16 @@
 
 namespace vs {
 
-constexpr int kScanWarps = 8;       // consumer warps per CTA
+constexpr int kMaxScanWarps = 16;   // upper bound on consumer warps per CTA (LDG variant)
+constexpr int kDefScanWarps = 12;   // default consumer warps (8 when the k-lists are large)
+constexpr int kMaxTmaWarps = 12;    // TMA variant: register budget of a 1-CTA/SM kernel
 constexpr int kMaxQB = 8;           // queries scored per pass over the database
+
+// consumer warps for a query block of `qb` with k-entry lists: 12 while the per-warp lists
+// (warps x qb x k x 8 B of shared memory) stay within 32 KB, else 8
+inline int scan_warps_for(int qb, int k) {
+  return (size_t)kDefScanWarps * qb * k * 8 <= 32 * 1024 ? kDefScanWarps : 8;
+}
 
 struct ScanParams {
   const void* db;          // fp32 rows (vec = 4 floats) or bf16 rows (vec = 8 bf16), 16 B vectors
@@ -20,12 +28,13 @@ struct ScanParams {
   int k;
   int epilogue;            // VS_METRIC_* of the epilogue (cosine divides by the row norm)
   const uint32_t* row_mask;
-  float* part_key;         // (QB, nlists, k) per-warp partial lists, sorted
+  float* part_key;         // (QB, nlists, k) per-CTA partial lists, sorted best first
   int32_t* part_id;
   uint32_t* tau;           // (QB,) shared pruning threshold, enc_key()-encoded, init enc(-inf)
-  int nlists;              // gridDim.x * kScanWarps
+  int nlists;              // gridDim.x
+  int warps;               // consumer warps per CTA (set by launch_scan)
   // TMA variant only
-  int tile_rows;           // rows per staged tile = kScanWarps * rows_per_warp
+  int tile_rows;           // rows per staged tile = warps * rows_per_warp
   int stages;
 };
 
@@ -50,6 +59,8 @@ struct MergeParams {
   int64_t chunk;           // candidates per contiguous chunk
   int64_t chunk_stride;    // elements between chunks of the same query
   int64_t query_stride;    // elements between queries inside a chunk
+  int list_len;            // > 0: candidates are consecutive lists of list_len entries sorted
+                           // best first (enables the head-sample pre-filter); 0: no structure
   int k;
   const uint32_t* tau;     // nullable: encoded lower bound on the k-th best key (pre-filter)
   int negate_in;           // candidates are distances: key = -score
@@ -63,7 +74,8 @@ int launch_merge(const MergeParams& p, int B, cudaStream_t stream);
 // scan-list layout: candidates of query b contiguous at b * per_query
 int launch_merge(const float* cand_key, const int32_t* cand_id, int64_t per_query, int B, int k,
                  const uint32_t* tau, int negate_scores, float* out_scores, int32_t* out_ids,
-                 int64_t out_stride, cudaStream_t stream, const int32_t* id_map = nullptr);
+                 int64_t out_stride, cudaStream_t stream, const int32_t* id_map = nullptr,
+                 int list_len = 0);
 
 // K5
 int launch_rescore(const float* rows, int ld, int dim, const float* norms, int metric,

@@ -38,7 +38,9 @@ static bool default_tma() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200VS_SCAN");
-    v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+    // measured on B200 (profiles/r01_scan_sweep.txt): direct 128-bit loads beat the
+    // TMA-staged ring at every shape, so LDG is the default; B200VS_SCAN=tma selects the ring
+    v = (e && strcmp(e, "tma") == 0) ? 1 : 0;
   }
   return v == 1;
 }
@@ -50,8 +52,8 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
                      int64_t out_stride, bool map_ids, cudaStream_t stream) {
   const int ldq = bf16 ? s->ld16 : s->ld;
   int qb_max = 8;
-  while (qb_max > 1 && (size_t)kScanWarps * qb_max * kk * 8 > 64 * 1024) qb_max >>= 1;
-  if ((size_t)kScanWarps * kk * 8 > 64 * 1024) {
+  while (qb_max > 1 && (size_t)8 * qb_max * kk * 8 > 64 * 1024) qb_max >>= 1;
+  if ((size_t)8 * kk * 8 > 64 * 1024) {
     set_error("invalid argument: k must be <= 1024");
     return VS_ERR_INVALID;
   }
@@ -99,7 +101,7 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
     if (int rc = launch_scan(p, qb, l2, bf16, use_tma, s->num_sms, &nl, nullptr, false, stream)) return rc;
     if (int rc = launch_merge(part_key, part_id, (int64_t)nl * kk, nb, kk, tau + b0, l2 ? 1 : 0,
                               out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride,
-                              out_stride, stream, map_ids ? s->id_map() : nullptr))
+                              out_stride, stream, map_ids ? s->id_map() : nullptr, kk))
       return rc;
   }
   return VS_OK;

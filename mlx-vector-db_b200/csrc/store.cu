@@ -304,7 +304,7 @@ int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_
   }
   s->max_rows = max_rows;
   int rc = s->rows.init(device, (size_t)max_rows * s->ld * 4);
-  if (!rc) rc = s->norms.init(device, (size_t)max_rows * 4);
+  if (!rc) rc = s->norms.init(device, (size_t)max_rows * 4 + 64);
   if (!rc) rc = s->sqnorms.init(device, (size_t)max_rows * 4);
   if (!rc && shadow) rc = s->shadow_rows.init(device, (size_t)max_rows * s->ld16 * 2);
   if (!rc) rc = s->gids.init(device, (size_t)max_rows * 4);
@@ -379,7 +379,8 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
   const int64_t n1 = n0 + m;
   if (n1 > s->max_rows) { set_error("store is full (max_rows reached)"); return VS_ERR_OOM; }
   if (int rc = s->rows.ensure((size_t)n1 * s->ld * 4, stream)) return rc;
-  if (int rc = s->norms.ensure((size_t)n1 * 4, stream)) return rc;
+  // + slack: the TMA scan copies norms in whole 16-byte granules past row n
+  if (int rc = s->norms.ensure((size_t)n1 * 4 + 64, stream)) return rc;
   if (int rc = s->sqnorms.ensure((size_t)n1 * 4, stream)) return rc;
   if (s->shadow)
     if (int rc = s->shadow_rows.ensure((size_t)n1 * s->ld16 * 2, stream)) return rc;

@@ -155,9 +155,9 @@ class ShardedVectorStore:
         self.shard.search_into(q, kk, pack)
         if self.world == 1:
             return pack[1], pack[0].view(torch.float32)
-        gathered = torch.empty((self.world,) + tuple(pack.shape), dtype=pack.dtype, device=pack.device)
-        dist.all_gather_into_tensor(gathered, pack, group=self.group)
-        return self.shard.merge(gathered, self.world, B, kk)
+        flat = torch.empty((self.world * pack.numel(),), dtype=pack.dtype, device=pack.device)
+        dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
+        return self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
 
     def close(self) -> None:
         self.shard.close()

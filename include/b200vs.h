@@ -164,6 +164,11 @@ VS_API int vs_normalize_rows(int device, const float* x, int64_t n, int dim, flo
 VS_API int vs_score_matrix(int device, int metric, const float* q, int B, const float* db,
                            int64_t n, int dim, float* out, void* stream);
 
+/* Test hook for K3: the full (B, count) matrix of tensor-core scores
+ * bf16(prep(q)) . bf16(shadow row) with fp32 accumulation, exactly what the GEMM path's
+ * epilogue filters.  `out` is a (B, count) fp32 DEVICE buffer.  Not used by the search path. */
+VS_API int vs_debug_gemm_scores(vs_store* s, const float* q, int B, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

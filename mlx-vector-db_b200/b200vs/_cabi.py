@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         "vs_fallback_count": (i64, [p]),
         "vs_merge": (i32, [i32, i32, f32p, i32p, i32, i32, i32, i64, f32p, i32p, p]),
         "vs_rescore": (i32, [p, f32p, i32, i32p, i32, i32, f32p, i32p, p]),
+        "vs_debug_gemm_scores": (i32, [p, f32p, i32, f32p, p]),
         "vs_normalize_rows": (i32, [i32, f32p, i64, i32, f32p, p]),
         "vs_score_matrix": (i32, [i32, i32, f32p, i32, f32p, i64, i32, f32p, p]),
     }

@@ -1,15 +1,801 @@
-// K3 placeholder: the tcgen05 path is not wired in yet; AUTO never selects it.
+// K3 gemm_topk -- large-batch search as a dense contraction on the 5th-gen tensor cores.
+//
+//   S'[q, r] = sum_k bf16(Q[q, k]) * bf16(X[r, k])        tcgen05.mma kind::f16, fp32 in TMEM
+//
+// replaces `matmul(Qn, DBn.T)` + `argsort(axis=1)[:, :k]` of the reference
+// (performance/mlx_optimized.py:86,235-236) without ever writing the (B, N) matrix:
+//
+//   pass 1  GEMM over a sample of the rows; epilogue keeps, per query, the maximum of every
+//           128-row tile.  The kc-th largest tile maximum is a lower bound tau[q] on the kc-th
+//           best score of the whole database (kc distinct rows reach it).
+//   pass 2  GEMM over all rows; epilogue compares TMEM columns with tau[q] (one thread owns
+//           one query: lane = query) and appends the rare survivors to that thread's private
+//           candidate buffer.
+//   then    K4 merge -> top-kc candidates by bf16 score; K5 rescoring in exact fp32 with the
+//           scan's arithmetic; final K4 merge -> top-k; certification: the candidate set
+//           provably contains the exact top-k when
+//               exact_k-th  >  bf16_kc-th + E,   E >= |exact - bf16| for every row,
+//           otherwise (or if a candidate buffer overflowed) the query is re-run through the
+//           exact fp32 scan (K2).  Results are therefore always the exact fp32 ones.
+//
+// Kernel anatomy (one CTA per SM, 256 threads): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quadrant =
+// warp % 4).  Operands are bf16, K-major, 128-byte swizzled: one "chunk" is 128 rows x 64
+// elements = 16 KB, loaded by one cp.async.bulk.tensor.2d.
+//   RESIDENT (K <= 256): the CTA's query tiles (up to 4 x 128 queries) are loaded once and stay
+//     in shared memory; database tiles of 128 rows stream through a ring; 4 TMEM accumulators
+//     of 128 columns, one per query tile, let the epilogue of tile m overlap the MMAs of m+1.
+//   STREAMING (any K): query and database chunks both stream through the ring per 64-wide K
+//     step; database tiles of 256 rows; 2 TMEM accumulators of 256 columns.
+#include <cuda.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
 #include "gemm_topk.cuh"
+#include "scan_topk.cuh"
 #include "store.cuh"
 
 namespace vs {
 
-bool gemm_supported(const vs_store*, int64_t, int, int) { return false; }
+constexpr int kGemmThreads = 256;
+constexpr int kTileM = 128;              // queries per m-tile = TMEM lanes
+constexpr int kChunkK = 64;              // bf16 elements per 128-byte swizzled row
+constexpr int kChunkBytes = 128 * 128;   // 128 rows x 128 B
+constexpr int kTmemCols = 512;
+constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
+constexpr int kMaxQueriesPerLaunch = 2048;
 
-int gemm_path(vs_store*, int64_t, const float*, int, int, bool, bool, float*, int32_t*, int64_t,
-              cudaStream_t) {
-  set_error("the GEMM search path is not available in this build");
-  return VS_ERR_STATE;
+enum { kModeFilter = 0, kModeMax = 1, kModeDump = 2 };
+
+struct GemmParams {
+  int kchunks;              // K / 64
+  int64_t n_rows;           // database rows visible
+  int n_tiles;              // database tiles this launch covers (tile = TN rows)
+  int m_tiles;              // query tiles in the batch
+  int ngroups;              // RESIDENT: query groups (CTA c serves group c % ngroups)
+  int nq;                   // live queries
+  int mode;
+  int stages;               // ring depth
+  const float* tau;         // (nq,) filter threshold (kModeFilter)
+  float* cand_score;        // (lists, m_tiles*128, kCandCap)
+  int32_t* cand_id;
+  int32_t* cand_cnt;        // STREAMING only: (lists, m_tiles*128) running counts, zeroed by the host
+  int32_t* overflow;        // (m_tiles*128,) set to 1 when a buffer overflowed
+  float* gmax;              // kModeMax: (m_tiles*128, n_tiles)
+  float* dump;              // kModeDump: (nq, dump_ld)
+  int64_t dump_ld;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
+// [46,48), layout_type=2 [61,64))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// -------------------------------------------------------------------- the kernel
+// MT > 0: RESIDENT with MT query tiles per CTA, TN = 128.  MT == 0: STREAMING, TN = 256.
+template <int MT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                 const GemmParams p) {
+  constexpr bool RES = MT > 0;
+  constexpr int TN = RES ? 128 : 256;
+  constexpr int SLOTS = kTmemCols / TN;
+  constexpr int B_CHUNK_BYTES = TN * 128;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  unsigned char* smem = smem_raw + ((1024 - (s_u32(smem_raw) & 1023)) & 1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kch = p.kchunks;
+
+  // ---- carve-up
+  unsigned char* a_res = smem;                                         // RES: MT*kch chunks
+  const size_t a_bytes = RES ? (size_t)MT * kch * kChunkBytes : 0;
+  const size_t stage_bytes = RES ? (size_t)kch * B_CHUNK_BYTES : (size_t)kChunkBytes + B_CHUNK_BYTES;
+  unsigned char* ring = smem + a_bytes;
+  unsigned char* tail = ring + (size_t)p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  // bars: [0]=a_full, [1..S]=full, [1+S..2S]=empty, then acc_full[SLOTS], acc_empty[SLOTS]
+  const uint32_t bar_a = s_u32(bars);
+  const uint32_t bar_full = s_u32(bars + 1);
+  const uint32_t bar_empty = s_u32(bars + 1 + p.stages);
+  const uint32_t bar_accf = s_u32(bars + 1 + 2 * p.stages);
+  const uint32_t bar_acce = s_u32(bars + 1 + 2 * p.stages + SLOTS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * p.stages + 2 * SLOTS);
+
+  // ---- work assignment
+  const int ngroups = RES ? p.ngroups : 1;
+  const int group = blockIdx.x % ngroups;
+  const int cig = blockIdx.x / ngroups;                                // CTA index inside its group
+  const int ctas_in_group = (gridDim.x - group + ngroups - 1) / ngroups;
+  const int m_first = RES ? group * MT : 0;
+  const int m_count = RES ? min(MT, p.m_tiles - m_first) : p.m_tiles;
+  int my_tiles = 0;
+  if (cig < p.n_tiles) my_tiles = (p.n_tiles - cig + ctas_in_group - 1) / ctas_in_group;
+
+  if (threadIdx.x == 0) {
+    bar_init(bar_a, 1);
+    for (int i = 0; i < p.stages; ++i) { bar_init(bar_full + 8 * i, 1); bar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < SLOTS; ++i) { bar_init(bar_accf + 8 * i, 1); bar_init(bar_acce + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
+                 "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0 && my_tiles > 0 && m_count > 0) {
+      if (RES) {
+        bar_expect_tx(bar_a, (uint32_t)(m_count * kch * kChunkBytes));
+        for (int mt = 0; mt < m_count; ++mt)
+          for (int kc = 0; kc < kch; ++kc)
+            tma_load_2d(s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes), &map_q, kc * kChunkK,
+                        (m_first + mt) * kTileM, bar_a);
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int nt = cig + i * ctas_in_group;
+        if (RES) {
+          bar_wait(bar_empty + 8 * st, ph ^ 1u);
+          bar_expect_tx(bar_full + 8 * st, (uint32_t)(kch * B_CHUNK_BYTES));
+          for (int kc = 0; kc < kch; ++kc)
+            tma_load_2d(s_u32(ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES), &map_x,
+                        kc * kChunkK, nt * TN, bar_full + 8 * st);
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
+        } else {
+          for (int mt = 0; mt < m_count; ++mt)
+            for (int kc = 0; kc < kch; ++kc) {
+              bar_wait(bar_empty + 8 * st, ph ^ 1u);
+              bar_expect_tx(bar_full + 8 * st, (uint32_t)(kChunkBytes + B_CHUNK_BYTES));
+              unsigned char* dst = ring + (size_t)st * stage_bytes;
+              tma_load_2d(s_u32(dst), &map_q, kc * kChunkK, mt * kTileM, bar_full + 8 * st);
+              // database tile of 256 rows = two boxes of 128 rows
+              tma_load_2d(s_u32(dst + kChunkBytes), &map_x, kc * kChunkK, nt * TN, bar_full + 8 * st);
+              tma_load_2d(s_u32(dst + 2 * kChunkBytes), &map_x, kc * kChunkK, nt * TN + 128, bar_full + 8 * st);
+              if (++st == p.stages) { st = 0; ph ^= 1u; }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0 && my_tiles > 0 && m_count > 0) {
+      constexpr uint32_t idesc = instr_desc(kTileM, TN);
+      if (RES) bar_wait(bar_a, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      int it = 0;                                       // (n-tile, m-tile) sequence number
+      for (int i = 0; i < my_tiles; ++i) {
+        if (RES) {
+          bar_wait(bar_full + 8 * st, ph);
+          tc_fence_after();
+        }
+        for (int mt = 0; mt < m_count; ++mt, ++it) {
+          const int slot = it % SLOTS;
+          const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
+          bar_wait(bar_acce + 8 * slot, aph ^ 1u);      // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TN);
+          for (int kc = 0; kc < kch; ++kc) {
+            uint32_t a_addr, b_addr;
+            if (RES) {
+              a_addr = s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes);
+              b_addr = s_u32(ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES);
+            } else {
+              bar_wait(bar_full + 8 * st, ph);
+              tc_fence_after();
+              a_addr = s_u32(ring + (size_t)st * stage_bytes);
+              b_addr = a_addr + kChunkBytes;
+            }
+            const uint64_t a_desc = smem_desc(a_addr);
+            const uint64_t b_desc = smem_desc(b_addr);
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)      // +32 B per 16-element K step
+              tc_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                     (kc | k) != 0 ? 1u : 0u);
+            if (!RES) {
+              tc_commit(bar_empty + 8 * st);            // smem stage free once these MMAs retire
+              if (++st == p.stages) { st = 0; ph ^= 1u; }
+            }
+          }
+          tc_commit(bar_accf + 8 * slot);               // accumulator ready for the epilogue
+        }
+        if (RES) {
+          tc_commit(bar_empty + 8 * st);
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+    const int row = quad * 32 + lane;                   // query row inside the m-tile
+    const int lists = RES ? ctas_in_group : (int)gridDim.x;
+    const int list = RES ? cig : (int)blockIdx.x;
+    const int64_t q_total = (int64_t)p.m_tiles * kTileM;
+    int cnt[RES ? MT : 1];
+    float tau[RES ? MT : 1];
+    if (RES) {
+#pragma unroll
+      for (int mt = 0; mt < (RES ? MT : 1); ++mt) {
+        cnt[mt] = 0;
+        const int q = (m_first + mt) * kTileM + row;
+        tau[mt] = (p.mode == kModeFilter && q < p.nq) ? p.tau[q] : __int_as_float(0x7f800000);
+      }
+    }
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int nt = cig + i * ctas_in_group;
+#pragma unroll
+      for (int mtu = 0; mtu < (RES ? MT : 1); ++mtu) {
+        // RESIDENT: statically unrolled over the CTA's query tiles (state in registers);
+        // STREAMING: dynamic loop over all query tiles (state in global memory)
+        const int m_lo = RES ? mtu : 0;
+        const int m_hi = RES ? (mtu < m_count ? mtu + 1 : mtu) : m_count;
+        for (int mt = m_lo; mt < m_hi; ++mt, ++it) {
+          const int slot = it % SLOTS;
+          const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
+          const int q = (m_first + mt) * kTileM + row;
+          float t;
+          int c;
+          if (RES) { t = tau[mtu]; c = cnt[mtu]; }
+          else {
+            t = (p.mode == kModeFilter && q < p.nq) ? p.tau[q] : __int_as_float(0x7f800000);
+            c = p.mode == kModeFilter ? p.cand_cnt[(int64_t)list * q_total + q] : 0;
+          }
+          bar_wait(bar_accf + 8 * slot, aph);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
+          const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
+          float rmax = VS_NEG_INF;
+#pragma unroll 1
+          for (int c0 = 0; c0 < TN; c0 += 32) {
+            float v[32];
+            tc_ld32(taddr + (uint32_t)c0, v);
+            tc_wait_ld();
+            if (c0 + 32 == TN) {                        // accumulator fully read: hand it back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) bar_arrive(bar_acce + 8 * slot);
+            }
+            if (p.mode == kModeDump) {
+              if (q < p.nq) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int64_t r = (int64_t)nt * TN + c0 + j;
+                  if (r < p.n_rows) p.dump[(int64_t)q * p.dump_ld + r] = v[j];
+                }
+              }
+              continue;
+            }
+            float m01 = fmaxf(v[0], v[1]);
+#pragma unroll
+            for (int j = 2; j < 32; j += 2) m01 = fmaxf(m01, fmaxf(v[j], v[j + 1]));
+            if (p.mode == kModeMax) { rmax = fmaxf(rmax, m01); continue; }
+            if (m01 >= t) {
+              const int64_t r0 = (int64_t)nt * TN + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (v[j] >= t && r0 + j < p.n_rows) {
+                  if (c < kCandCap) {
+                    p.cand_score[cbase + c] = v[j];
+                    p.cand_id[cbase + c] = (int32_t)(r0 + j);
+                  }
+                  ++c;
+                }
+              }
+            }
+          }
+          if (p.mode == kModeMax && q < q_total) p.gmax[(int64_t)q * p.n_tiles + nt] = rmax;
+          if (RES) cnt[mtu] = c;
+          else if (p.mode == kModeFilter) p.cand_cnt[(int64_t)list * q_total + q] = c;
+        }
+      }
+    }
+    // close the candidate lists: unused slots get id -1
+    if (p.mode == kModeFilter) {
+#pragma unroll
+      for (int mtu = 0; mtu < (RES ? MT : 1); ++mtu) {
+        const int m_lo = RES ? mtu : 0;
+        const int m_hi = RES ? (mtu < m_count ? mtu + 1 : mtu) : m_count;
+        for (int mt = m_lo; mt < m_hi; ++mt) {
+          const int q = (m_first + mt) * kTileM + row;
+          const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
+          int c = RES ? cnt[mtu] : p.cand_cnt[(int64_t)list * q_total + q];
+          if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }
+          for (int e = c; e < kCandCap; ++e) p.cand_id[cbase + e] = -1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------ small helper kernels
+// queries -> bf16 (normalised for cosine), padded to (m_tiles*128, ld16); also the per-query
+// rounding-error norm ||u - bf16(u)|| and ||u|| for the certification bound
+__global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int dim, int metric, int ld16,
+                                         int rows_padded, __nv_bfloat16* __restrict__ out,
+                                         float* __restrict__ qerr, float* __restrict__ qlen) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= rows_padded) return;
+  __nv_bfloat16* dst = out + (size_t)b * ld16;
+  if (b >= B) {
+    for (int c = lane; c < ld16; c += 32) dst[c] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float* src = q + (size_t)b * dim;
+  float acc = 0.f;
+  for (int c = lane; c < dim; c += 32) { const float v = src[c]; acc = fmaf(v, v, acc); }
+  const float nrm = fmaxf(sqrtf(warp_sum(acc)), 1e-8f);
+  float e2 = 0.f, u2 = 0.f;
+  for (int c = lane; c < ld16; c += 32) {
+    float v = c < dim ? src[c] : 0.f;
+    if (metric == VS_METRIC_COSINE) v = v / nrm;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[c] = h;
+    const float d = v - __bfloat162float(h);
+    e2 = fmaf(d, d, e2);
+    u2 = fmaf(v, v, u2);
+  }
+  e2 = warp_sum(e2);
+  u2 = warp_sum(u2);
+  if (lane == 0) { qerr[b] = sqrtf(e2) * 1.00001f; qlen[b] = sqrtf(u2) * 1.00001f; }
+}
+
+// certification + compaction of the queries that need the exact fallback
+__global__ void certify_kernel(int B, int k, int kc, int64_t n_rows, const float* __restrict__ cand_s,
+                               const int32_t* __restrict__ cand_i, const float* __restrict__ tau,
+                               const int32_t* __restrict__ overflow, const float* __restrict__ out_s,
+                               const int32_t* __restrict__ out_i, int64_t out_stride,
+                               const float* __restrict__ qerr, const float* __restrict__ qlen,
+                               const uint32_t* __restrict__ bounds, float slack, int* __restrict__ n_bad,
+                               int32_t* __restrict__ bad_list) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float max_err = __uint_as_float(bounds[0]);
+  const float max_len = __uint_as_float(bounds[1]);
+  // |exact - bf16| <= ||u|| * max||v - v^|| + ||u - u^|| * max||v^|| (+ fp32 accumulation slack)
+  const float E = qlen[b] * max_err + qerr[b] * max_len + slack * (1.f + qlen[b] * max_len);
+  // bf16 score no row outside the candidate set can exceed
+  const bool full = cand_i[(int64_t)b * kc + kc - 1] >= 0;
+  const float beta = full ? cand_s[(int64_t)b * kc + kc - 1] : tau[b];
+  const int kk = (int)(n_rows < k ? n_rows : k);
+  bool ok = overflow[b] == 0;
+  if (ok) {
+    if (!full && n_rows <= kc) ok = true;              // every row is a candidate
+    else {
+      const bool have_k = out_i[(int64_t)b * out_stride + kk - 1] >= 0;
+      ok = have_k && out_s[(int64_t)b * out_stride + kk - 1] > beta + E;
+    }
+  }
+  if (!ok) bad_list[atomicAdd(n_bad, 1)] = b;
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+__global__ void gather_queries_kernel(const float* __restrict__ q, int dim, const int32_t* __restrict__ idx,
+                                      int n, float* __restrict__ out) {
+  const int64_t total = (int64_t)n * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = q[(int64_t)idx[i / dim] * dim + i % dim];
+}
+__global__ void scatter_results_kernel(const float* __restrict__ ts, const int32_t* __restrict__ ti, int k,
+                                       const int32_t* __restrict__ idx, int n, float* __restrict__ out_s,
+                                       int32_t* __restrict__ out_i, int64_t out_stride) {
+  const int64_t total = (int64_t)n * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = (int64_t)idx[i / k] * out_stride + i % k;
+    out_s[o] = ts[i];
+    out_i[o] = ti[i];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  });
+  return fn;
+}
+
+// (rows, K) bf16 row-major matrix, boxes of 128 rows x 64 elements, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VS_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kChunkK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return VS_ERR_CUDA; }
+  return VS_OK;
+}
+
+struct GemmPlan {
+  int mt;            // resident query tiles per CTA (0 = streaming)
+  int stages;
+  size_t smem;
+  int tn;
+};
+
+static bool plan_gemm(int kchunks, int m_tiles, GemmPlan* plan) {
+  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/;
+  if (kchunks <= 4) {   // K <= 256: resident queries
+    int mt = kchunks <= 2 ? 4 : 1;
+    if (mt > m_tiles) mt = m_tiles >= 2 ? 2 : 1;
+    const size_t a = (size_t)mt * kchunks * kChunkBytes;
+    const size_t stage = (size_t)kchunks * kChunkBytes;
+    int stages = (int)((limit - a) / stage);
+    if (stages > 4) stages = 4;
+    if (stages >= 2) { *plan = {mt, stages, a + stages * stage + 1024 + 512, 128}; return true; }
+  }
+  const size_t stage = (size_t)3 * kChunkBytes;   // query chunk + 256-row database chunk
+  int stages = (int)(limit / stage);
+  if (stages > 6) stages = 6;
+  *plan = {0, stages, stages * stage + 1024 + 512, 256};
+  return true;
+}
+
+template <int MT>
+static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
+                         cudaStream_t stream) {
+  auto kern = gemm_topk_kernel<MT>;
+  VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(kProfGemm, stream);
+    kern<<<grid, kGemmThreads, smem, stream>>>(mq, mx, p);
+  }
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
+}
+
+static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,
+                       int num_sms, int* lists_out, cudaStream_t stream) {
+  p.stages = plan.stages;
+  int grid = num_sms;
+  if (plan.mt > 0) {
+    p.ngroups = (p.m_tiles + plan.mt - 1) / plan.mt;
+    const int64_t want = (int64_t)p.n_tiles * p.ngroups;
+    if (want < grid) grid = (int)want;
+    if (grid < p.ngroups) grid = p.ngroups;
+    if (lists_out) *lists_out = (grid + p.ngroups - 1) / p.ngroups;
+  } else {
+    p.ngroups = 1;
+    if (p.n_tiles < grid) grid = p.n_tiles;
+    if (lists_out) *lists_out = grid;
+  }
+  switch (plan.mt) {
+    case 0: return launch_gemm_t<0>(mq, mx, p, grid, plan.smem, stream);
+    case 1: return launch_gemm_t<1>(mq, mx, p, grid, plan.smem, stream);
+    case 2: return launch_gemm_t<2>(mq, mx, p, grid, plan.smem, stream);
+    case 4: return launch_gemm_t<4>(mq, mx, p, grid, plan.smem, stream);
+  }
+  set_error("internal: bad GEMM plan");
+  return VS_ERR_INVALID;
+}
+
+static int gemm_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200VS_GEMM"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return v;
+}
+static int gemm_min_batch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200VS_GEMM_MIN_BATCH"); v = e && *e ? atoi(e) : 48; }
+  return v;
+}
+
+// candidates kept for rescoring
+static int cand_count(int kk) { return std::max(2 * kk, kk + 22); }
+
+bool gemm_supported(const vs_store* s, int64_t n, int B, int kk) {
+  if (!gemm_enabled() || !s->shadow) return false;
+  if (s->metric == VS_METRIC_EUCLIDEAN) return false;       // L2 candidates: bf16 scan path
+  if (B < gemm_min_batch()) return false;
+  if (cand_count(kk) > 64) return false;
+  if (n < 65536) return false;                              // small stores: the scan is enough
+  return true;
+}
+
+struct Ws {
+  std::vector<std::pair<void**, size_t>> items;
+  unsigned char* base = nullptr;
+  cudaStream_t stream = nullptr;
+  template <typename T> void want(T** slot, size_t count) { items.push_back({(void**)slot, count * sizeof(T)}); }
+  int alloc(cudaStream_t st) {
+    stream = st;
+    size_t total = 0;
+    for (auto& it : items) total += (size_t)round_up((int64_t)it.second, 1024);
+    VS_CUDA(cudaMallocAsync((void**)&base, total ? total : 1024, st));
+    size_t off = 0;
+    for (auto& it : items) { *it.first = base + off; off += (size_t)round_up((int64_t)it.second, 1024); }
+    return VS_OK;
+  }
+  ~Ws() { if (base) cudaFreeAsync(base, stream); }
+};
+
+// exact fp32 scan of selected queries (defined in search.cu)
+int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, float* out_scores,
+                       int32_t* out_ids, int64_t out_stride, cudaStream_t stream);
+
+static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
+                      float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
+  const int K = s->ld16;
+  const int kch = K / kChunkK;
+  const int m_tiles = (B + kTileM - 1) / kTileM;
+  const int rows_padded = m_tiles * kTileM;
+  const int kc = (int)std::min<int64_t>(cand_count(kk), n);
+  GemmPlan plan;
+  plan_gemm(kch, m_tiles, &plan);
+  const int tn = plan.tn;
+  const int n_tiles = (int)((n + tn - 1) / tn);
+  // pass-1 sample: about 1/16 of the rows, at most 4096 tiles (merge kernel capacity), whole tiles
+  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>(n / 16 / tn, 4 * kc), 4096);
+  if (s_tiles > (int)(n / tn)) s_tiles = (int)(n / tn);
+  const bool sampled = s_tiles >= 2 * kc;
+
+  const int max_lists = s->num_sms;
+  Ws ws;
+  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *c1s, *rk; int32_t *ci, *ccnt, *c1i, *ovf, *bad; int* nbad;
+  ws.want(&qb, (size_t)rows_padded * K);
+  ws.want(&qerr, (size_t)rows_padded);
+  ws.want(&qlen, (size_t)rows_padded);
+  ws.want(&tau, (size_t)rows_padded);
+  ws.want(&gmax, sampled ? (size_t)rows_padded * s_tiles : 1);
+  ws.want(&cs, (size_t)max_lists * rows_padded * kCandCap);
+  ws.want(&ci, (size_t)max_lists * rows_padded * kCandCap);
+  ws.want(&ccnt, (size_t)max_lists * rows_padded);
+  ws.want(&c1s, (size_t)B * kc);
+  ws.want(&c1i, (size_t)B * kc);
+  ws.want(&rk, (size_t)B * kc);
+  ws.want(&ovf, (size_t)rows_padded);
+  ws.want(&bad, (size_t)B);
+  ws.want(&nbad, 1);
+  if (int rc = ws.alloc(stream)) return rc;
+
+  CUtensorMap mq, mx;
+  if (int rc = make_map(&mq, qb, rows_padded, K)) return rc;
+  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K)) return rc;
+
+  prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
+                                                                    qerr, qlen);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  VS_CUDA(cudaMemsetAsync(ovf, 0, (size_t)rows_padded * 4, stream));
+  VS_CUDA(cudaMemsetAsync(nbad, 0, 4, stream));
+
+  GemmParams p = {};
+  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B;
+  p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
+  if (plan.mt == 0) VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
+  if (sampled) {
+    // pass 1: per-query maxima of the sample tiles -> tau = kc-th largest (a lower bound of
+    // the kc-th best score overall)
+    p.mode = kModeMax; p.n_tiles = s_tiles; p.gmax = gmax;
+    if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
+    MergeParams m = {};
+    m.ck = gmax; m.ci = nullptr; m.per_query = s_tiles; m.chunk = s_tiles; m.chunk_stride = 0;
+    m.query_stride = s_tiles; m.list_len = 0; m.k = kc; m.tau = nullptr;
+    m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
+    if (int rc = launch_merge(m, B, stream)) return rc;
+    // tau[b] = c1s[b][kc-1]
+    VS_CUDA(cudaMemcpy2DAsync(tau, 4, c1s + (kc - 1), (size_t)kc * 4, 4, B, cudaMemcpyDeviceToDevice, stream));
+  } else {
+    // tiny store: no sample, every row is a candidate of the filter (tau = -inf)
+    fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, -__builtin_inff(), rows_padded);
+    count_launch();
+    VS_CHECK_LAUNCH();
+  }
+  // pass 2: threshold filter over all rows
+  int lists = 0;
+  p.mode = kModeFilter; p.n_tiles = n_tiles; p.gmax = nullptr;
+  if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, &lists, stream)) return rc;
+  // K4: best kc candidates by bf16 score
+  {
+    MergeParams m = {};
+    m.ck = cs; m.ci = ci; m.per_query = (int64_t)lists * kCandCap; m.chunk = kCandCap;
+    m.chunk_stride = (int64_t)rows_padded * kCandCap; m.query_stride = kCandCap; m.list_len = 0;
+    m.k = kc; m.tau = nullptr; m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
+    if (int rc = launch_merge(m, B, stream)) return rc;
+  }
+  // K5: exact fp32 scores of the candidates, then the final top-k
+  {
+    float* qprep = nullptr;
+    VS_CUDA(cudaMallocAsync((void**)&qprep, (size_t)B * s->ld * 4, stream));
+    int rc = launch_prep_queries(q, B, s->dim, s->metric, s->ld, false, 1.f, qprep, nullptr, nullptr, stream);
+    if (!rc) rc = launch_rescore((const float*)s->rows.ptr(), s->ld, s->dim, (const float*)s->norms.ptr(), s->metric,
+                                 qprep, s->ld, B, c1i, kc, rk, stream);
+    if (!rc) rc = launch_merge(rk, c1i, kc, B, kk, nullptr, 0, out_scores, out_ids, out_stride, stream, s->id_map());
+    cudaFreeAsync(qprep, stream);
+    if (rc) return rc;
+  }
+  if (!certify) return VS_OK;
+  // certification needs LOCAL row ids only through their validity (>= 0), so the id map does not matter
+  const float slack = 4.f * (float)s->dim * 5.9604645e-8f + 1e-6f;
+  certify_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, kk, kc, n, c1s, c1i, tau, ovf, out_scores, out_ids,
+                                                     out_stride, qerr, qlen, s->bounds, slack, nbad, bad);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  int h_bad = 0;
+  VS_CUDA(cudaMemcpyAsync(&h_bad, nbad, 4, cudaMemcpyDeviceToHost, stream));
+  VS_CUDA(cudaStreamSynchronize(stream));
+  if (h_bad == 0) return VS_OK;
+  s->fallbacks.fetch_add(h_bad);
+  // exact fp32 scan for the queries that could not be certified
+  float* gq = nullptr; float* ts = nullptr; int32_t* ti = nullptr;
+  VS_CUDA(cudaMallocAsync((void**)&gq, (size_t)h_bad * s->dim * 4, stream));
+  VS_CUDA(cudaMallocAsync((void**)&ts, (size_t)h_bad * kk * 4, stream));
+  VS_CUDA(cudaMallocAsync((void**)&ti, (size_t)h_bad * kk * 4, stream));
+  gather_queries_kernel<<<std::min(1184, (h_bad * s->dim + 255) / 256), 256, 0, stream>>>(q, s->dim, bad, h_bad, gq);
+  count_launch();
+  int rc = scan_queries_exact(s, n, gq, h_bad, kk, scan_tma, ts, ti, kk, stream);
+  if (!rc) {
+    scatter_results_kernel<<<std::min(1184, (h_bad * kk + 255) / 256), 256, 0, stream>>>(ts, ti, kk, bad, h_bad,
+                                                                                       out_scores, out_ids, out_stride);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "scatter_results_kernel", __FILE__, __LINE__);
+  }
+  cudaFreeAsync(gq, stream);
+  cudaFreeAsync(ts, stream);
+  cudaFreeAsync(ti, stream);
+  return rc;
+}
+
+int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
+              float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
+  if (!s->shadow) { set_error("store was created without a bf16 shadow copy"); return VS_ERR_STATE; }
+  if (s->metric == VS_METRIC_EUCLIDEAN) { set_error("the GEMM path serves cosine and dot_product"); return VS_ERR_STATE; }
+  if (cand_count(kk) > 64) { set_error("invalid argument: k too large for the GEMM path (k <= 32)"); return VS_ERR_INVALID; }
+  for (int b0 = 0; b0 < B; b0 += kMaxQueriesPerLaunch) {
+    const int nb = std::min(kMaxQueriesPerLaunch, B - b0);
+    if (int rc = gemm_block(s, n, q + (size_t)b0 * s->dim, nb, kk, certify, scan_tma,
+                            out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride, out_stride,
+                            stream))
+      return rc;
+  }
+  return VS_OK;
+}
+
+// test / API helper: the full (B, n) bf16 tensor-core score matrix (kModeDump)
+int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, int64_t ld, cudaStream_t stream) {
+  const int K = s->ld16;
+  const int kch = K / kChunkK;
+  const int m_tiles = (B + kTileM - 1) / kTileM;
+  const int rows_padded = m_tiles * kTileM;
+  GemmPlan plan;
+  plan_gemm(kch, m_tiles, &plan);
+  Ws ws;
+  __nv_bfloat16* qb; float *qerr, *qlen;
+  ws.want(&qb, (size_t)rows_padded * K);
+  ws.want(&qerr, (size_t)rows_padded);
+  ws.want(&qlen, (size_t)rows_padded);
+  if (int rc = ws.alloc(stream)) return rc;
+  CUtensorMap mq, mx;
+  if (int rc = make_map(&mq, qb, rows_padded, K)) return rc;
+  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K)) return rc;
+  prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
+                                                                    qerr, qlen);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  GemmParams p = {};
+  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B;
+  p.mode = kModeDump; p.n_tiles = (int)((n + plan.tn - 1) / plan.tn); p.dump = out; p.dump_ld = ld;
+  return launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream);
 }
 
 }  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_debug_gemm_scores(vs_store* s, const float* q, int B, float* out, void* stream_) {
+  VS_REQUIRE(s != nullptr && q != nullptr && out != nullptr, "NULL pointer");
+  VS_REQUIRE(B > 0, "B must be > 0");
+  if (!s->shadow) { set_error("store was created without a bf16 shadow copy"); return VS_ERR_STATE; }
+  VS_CUDA(cudaSetDevice(s->device));
+  const int64_t n = s->count.load(std::memory_order_acquire);
+  VS_REQUIRE(n > 0, "store is empty");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (s->append_done && s->append_stream != stream) VS_CUDA(cudaStreamWaitEvent(stream, s->append_done, 0));
+  return gemm_dump_scores(s, n, q, B, out, n, stream);
+}

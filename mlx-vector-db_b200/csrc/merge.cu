@@ -21,7 +21,7 @@ __device__ __forceinline__ int64_t cand_addr(const MergeParams& p, int b, int64_
 __device__ __forceinline__ bool cand_load(const MergeParams& p, int b, int64_t i, float thr,
                                           float& key, int& id) {
   const int64_t a = cand_addr(p, b, i);
-  id = p.ci[a];
+  id = p.ci ? p.ci[a] : (int)i;     // no id array: the id is the candidate's position
   if (id < 0) return false;
   key = p.ck[a];
   if (p.negate_in) key = -key;
@@ -55,12 +55,15 @@ __device__ __forceinline__ void smem_bitonic(float* sk, int* si, int n2, int tid
 }
 
 constexpr int kRankCap = 1024;   // up to this many items are ordered by counting ranks
+constexpr int kHistBins = 1024;  // linear bins of the histogram select
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_topk_kernel(const MergeParams p) {
   __shared__ float sk[kMergeCap];
   __shared__ int si[kMergeCap];
   __shared__ int cnt;
+  __shared__ int cut_bin;
+  __shared__ int hist[kHistBins];
   __shared__ float thr_sh;
   __shared__ float red_k[kMergeThreads / 32];
   __shared__ int red_i[kMergeThreads / 32];
@@ -85,7 +88,7 @@ merge_topk_kernel(const MergeParams p) {
         float key = VS_NEG_INF;
         if (i < L) {
           const int64_t a = cand_addr(p, b, (int64_t)i * p.list_len + pos - 1);
-          if (p.ci[a] >= 0) key = p.negate_in ? -p.ck[a] : p.ck[a];
+          if (!p.ci || p.ci[a] >= 0) key = p.negate_in ? -p.ck[a] : p.ck[a];
         }
         sk[i] = key;
       }
@@ -117,7 +120,78 @@ merge_topk_kernel(const MergeParams p) {
     }
   }
   __syncthreads();
-  const int n = cnt;
+  int n = cnt;
+  // Histogram select: many survivors, few wanted.  Bin the keys linearly between their min
+  // and max (a monotone map), find the highest bin edge with at least k keys at or above it
+  // and keep only those -- typically a little more than k -- for the exact ordering below.
+  if (n > 256 && n <= kMergeCap && n > 2 * k) {
+    float lo = __int_as_float(0x7f800000), hi = VS_NEG_INF;
+    for (int i = tid; i < n; i += kMergeThreads) { lo = fminf(lo, sk[i]); hi = fmaxf(hi, sk[i]); }
+    for (int off = 16; off; off >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((tid & 31) == 0) { red_k[tid >> 5] = lo; red_i[tid >> 5] = __float_as_int(hi); }
+    for (int i = tid; i < kHistBins; i += kMergeThreads) hist[i] = 0;
+    __syncthreads();
+    lo = red_k[0]; hi = __int_as_float(red_i[0]);
+    for (int w = 1; w < kMergeThreads / 32; ++w) {
+      lo = fminf(lo, red_k[w]);
+      hi = fmaxf(hi, __int_as_float(red_i[w]));
+    }
+    if (hi > lo && hi - lo < 3.0e38f) {
+      const float scale = (float)(kHistBins - 1) / (hi - lo);
+      constexpr int kPer = kMergeCap / kMergeThreads;
+      float rk[kPer];
+      int ri[kPer], rb[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kMergeThreads;
+        rb[j] = -1;
+        if (i < n) {
+          rk[j] = sk[i]; ri[j] = si[i];
+          int bin = (int)((rk[j] - lo) * scale);
+          bin = bin < 0 ? 0 : (bin > kHistBins - 1 ? kHistBins - 1 : bin);
+          rb[j] = bin;
+          atomicAdd(&hist[bin], 1);
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {   // suffix sums over 32 bins per lane, then locate the crossing bin
+        constexpr int kSpan = kHistBins / 32;
+        int mine = 0;
+        for (int j = 0; j < kSpan; ++j) mine += hist[tid * kSpan + j];
+        int above = 0;   // keys in the bins of higher lanes
+        for (int l = 31; l > 0; --l) {
+          const int v = __shfl_sync(0xffffffffu, mine, l);
+          if (tid < l) above += v;
+        }
+        const bool cross = above < k && above + mine >= k;
+        const unsigned who = __ballot_sync(0xffffffffu, cross);
+        if (who == 0) { if (tid == 0) cut_bin = 0; }
+        else if (cross) {
+          int acc = above, bstar = tid * kSpan;
+          for (int j = kSpan - 1; j >= 0; --j) {
+            acc += hist[tid * kSpan + j];
+            if (acc >= k) { bstar = tid * kSpan + j; break; }
+          }
+          cut_bin = bstar;
+        }
+        if (tid == 0) cnt = 0;
+      }
+      __syncthreads();
+      const int cb = cut_bin;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        if (rb[j] >= cb) {
+          const int pos = atomicAdd(&cnt, 1);
+          sk[pos] = rk[j]; si[pos] = ri[j];
+        }
+      }
+      __syncthreads();
+      n = cnt;
+    }
+  }
   int written = 0;
   if (n <= kRankCap) {
     // order by counting: rank = number of better survivors; the first k ranks are written

@@ -107,6 +107,12 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
   return VS_OK;
 }
 
+// exact fp32 scan of a query set (the GEMM path's fallback for uncertified queries)
+int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, float* out_scores,
+                       int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
+  return scan_path(s, n, q, B, kk, false, use_tma, nullptr, out_scores, out_ids, out_stride, true, stream);
+}
+
 // exact fp32 rescoring of (B, kc) candidate ids + final ordering into (B, out_stride)
 static int rescore_path(vs_store* s, const float* q, int B, const int32_t* cand, int kc, int kk,
                         float* out_scores, int32_t* out_ids, int64_t out_stride,

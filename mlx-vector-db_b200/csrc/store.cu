@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(256)
 append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
                    int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
                    float* __restrict__ sqnorms, __nv_bfloat16* __restrict__ shadow, int ld16,
-                   int normalize_shadow, int32_t* __restrict__ gids, int64_t gid0) {
+                   int normalize_shadow, int32_t* __restrict__ gids, int64_t gid0,
+                   uint32_t* __restrict__ bounds) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -223,11 +224,25 @@ append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restr
       if (gids != nullptr) gids[n0 + r] = (int32_t)(gid0 + r);
     }
     if (shadow != nullptr) {
+      // bf16 shadow row + what the GEMM path's certification needs: the largest rounding
+      // error norm ||v - bf16(v)|| and the largest shadow norm ||bf16(v)|| over all rows
       __nv_bfloat16* sh = shadow + (n0 + r) * (int64_t)ld16;
+      float e2 = 0.f, s2 = 0.f;
       for (int c = lane; c < ld16; c += 32) {
         float v = c < dim ? s[c] : 0.f;
         if (normalize_shadow) v = v / nrm;
-        sh[c] = __float2bfloat16_rn(v);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        sh[c] = h;
+        const float vb = __bfloat162float(h);
+        const float dlt = v - vb;
+        e2 = fmaf(dlt, dlt, e2);
+        s2 = fmaf(vb, vb, s2);
+      }
+      e2 = warp_sum(e2);
+      s2 = warp_sum(s2);
+      if (lane == 0) {   // non-negative floats order like their bit patterns
+        atomicMax(bounds + 0, __float_as_uint(sqrtf(e2) * 1.00001f));
+        atomicMax(bounds + 1, __float_as_uint(sqrtf(s2) * 1.00001f));
       }
     }
   }
@@ -318,6 +333,8 @@ int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_
   cudaGetLastError();
   s->pinned_bytes = 1u << 20;
   cudaError_t e = cudaEventCreateWithFlags(&s->append_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->bounds, 16);
+  if (e == cudaSuccess) e = cudaMemset(s->bounds, 0, 16);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMallocHost(&s->pinned_in, s->pinned_bytes);
   if (e == cudaSuccess) e = cudaMallocHost(&s->pinned_out, s->pinned_bytes);
@@ -335,6 +352,7 @@ int vs_destroy(vs_store* s) {
   s->sqnorms.destroy();
   s->shadow_rows.destroy();
   s->gids.destroy();
+  if (s->bounds) cudaFree(s->bounds);
   if (s->append_done) cudaEventDestroy(s->append_done);
   if (s->host_stream) cudaStreamDestroy(s->host_stream);
   if (s->pinned_in) cudaFreeHost(s->pinned_in);
@@ -358,6 +376,8 @@ int vs_reset(vs_store* s) {
   std::lock_guard<std::mutex> g(s->mu);
   s->count.store(0, std::memory_order_release);
   s->mapped = false;
+  VS_CUDA(cudaSetDevice(s->device));
+  VS_CUDA(cudaMemset(s->bounds, 0, 16));
   return VS_OK;
 }
 
@@ -428,7 +448,8 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
         ksrc, ksrc_ld, master, s->ld, s->dim, n0 + off, mm, (float*)s->norms.ptr(),
         (float*)s->sqnorms.ptr(), s->shadow ? (__nv_bfloat16*)s->shadow_rows.ptr() : nullptr,
         s->ld16, s->metric == VS_METRIC_COSINE ? 1 : 0,
-        with_ids ? (int32_t*)s->gids.ptr() : nullptr, with_ids ? first_global_id + off : 0);
+        with_ids ? (int32_t*)s->gids.ptr() : nullptr, with_ids ? first_global_id + off : 0,
+        s->bounds);
     count_launch();
     VS_CHECK_LAUNCH();
     if (staging) VS_CUDA(cudaFreeAsync(staging, stream));

@@ -55,6 +55,7 @@ struct vs_store {
   vs::Arena norms;               // max(||x||, 1e-8), (N,)
   vs::Arena sqnorms;             // ||x||^2, (N,)
   vs::Arena shadow_rows;         // bf16, (N, ld16): x/max(||x||,1e-8) for cosine, x otherwise
+  uint32_t* bounds = nullptr;    // device: float bits of max ||v - bf16(v)||, max ||bf16(v)||
   vs::Arena gids;                // int32 global id per local row (row-sharded stores only)
   bool mapped = false;           // true once an append supplied global ids
   const int32_t* id_map() const { return mapped ? (const int32_t*)gids.ptr() : nullptr; }

@@ -1,0 +1,144 @@
+"""GPU: K3, the tcgen05/TMEM GEMM path (large query batches).
+
+1. The raw tensor-core scores (test hook vs_debug_gemm_scores) equal a torch restatement of
+   the same arithmetic: bf16-rounded normalised operands, fp32 accumulation (tolerance 2e-5:
+   only the accumulation order differs).  This pins TMA maps, swizzled shared-memory
+   descriptors, the instruction descriptor and the TMEM read-back for both kernel variants
+   (RESIDENT K <= 256, STREAMING any K), ragged B / N / D.
+2. The certified search (mode `gemm`) matches the CPU oracle like the fp32 scan does: ids exact
+   outside 1e-6 ties, scores within 1e-5 -- its results are fp32-rescored and every query
+   that cannot be proven exact is re-run through the exact scan."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import compare, datasets, vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_reference(q, db, metric):
+    qd = torch.from_numpy(q).cuda()
+    xd = torch.from_numpy(db).cuda()
+    if metric == "cosine":
+        qd = qd / qd.norm(dim=1, keepdim=True).clamp_min(1e-8)
+        xd = xd / xd.norm(dim=1, keepdim=True).clamp_min(1e-8)
+    qb = qd.to(torch.bfloat16).to(torch.float32)
+    xb = xd.to(torch.bfloat16).to(torch.float32)
+    return (qb.double() @ xb.double().T).float()
+
+
+DUMP_SHAPES = [
+    # N, D, B
+    (1000, 128, 5),        # resident, one query tile, ragged N
+    (4096, 128, 128),
+    (5000, 128, 300),      # resident, 3 query tiles (group of 4)
+    (3000, 128, 700),      # two query groups
+    (2500, 64, 130),       # K = 64: one chunk
+    (2000, 100, 17),       # D padded to 128
+    (1500, 256, 140),      # K = 256: resident with one tile per CTA
+    (1111, 384, 200),      # streaming
+    (700, 768, 129),       # streaming, 12 K-chunks
+    (40000, 128, 256),     # many tiles per CTA: ring and accumulator phases wrap
+    (30000, 384, 256),
+]
+
+
+@pytest.mark.parametrize("shape", DUMP_SHAPES, ids=[f"N{n}_D{d}_B{b}" for n, d, b in DUMP_SHAPES])
+@pytest.mark.parametrize("metric", ["cosine", "dot_product"])
+def test_tensor_core_scores_match_bf16_reference(make_store, shape, metric):
+    from b200vs import _cabi
+    n, d, B = shape
+    db = datasets.make_db(n, d)
+    q = datasets.make_queries(B, d)
+    st = make_store(d, metric)
+    st.add_vectors(db, [])
+    qd = torch.from_numpy(q).cuda()
+    out = torch.full((B, n), float("nan"), dtype=torch.float32, device="cuda")
+    _cabi.check(_cabi.lib().vs_debug_gemm_scores(st._handle, C.c_void_p(qd.data_ptr()), B,
+                                                 C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = _bf16_reference(q, db, metric)
+    assert not torch.isnan(out).any(), "some scores were never written"
+    scale = 1.0 if metric == "cosine" else float(ref.abs().max())
+    err = (out - ref).abs()
+    # the tensor core sums products in fp32 without per-step round-to-nearest: grows with K
+    tol = 2e-5 * max(1.0, d / 256) * scale
+    # torch's fp32 normalisation can differ from the append kernel's by one ulp, which now and
+    # then flips the bf16 rounding of one element (a 2^-8 relative step): tolerate a handful
+    # of such entries, bounded by one bf16 ulp of one product
+    outliers = int((err > tol).sum())
+    assert outliers <= max(4, int(2e-5 * err.numel())), (outliers, float(err.max()))
+    assert float(err.max()) <= 2e-3 * scale, float(err.max())
+
+
+SEARCH_SHAPES = [
+    # N, D, B, k
+    (70000, 128, 64, 10),
+    (100000, 128, 256, 10),
+    (80000, 128, 1024, 10),
+    (66000, 96, 130, 5),
+    (70001, 256, 200, 10),
+    (66000, 384, 128, 10),     # streaming kernel
+    (66000, 768, 64, 1),
+    (90000, 128, 100, 32),     # largest k the path takes (kc = 64)
+]
+
+
+@pytest.mark.parametrize("shape", SEARCH_SHAPES, ids=[f"N{n}_D{d}_B{b}_k{k}" for n, d, b, k in SEARCH_SHAPES])
+@pytest.mark.parametrize("metric", ["cosine", "dot_product"])
+def test_certified_gemm_search_matches_oracle(make_store, shape, metric):
+    from b200vs import _cabi
+    n, d, B, k = shape
+    db = datasets.make_db(n, d)
+    q = datasets.make_queries(B, d)
+    st = make_store(d, metric)
+    st.add_vectors(db, [])
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, metric)
+    ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["gemm"])
+    rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
+    assert rep.ok, f"{rep}"
+    # identical to the exact scan, bit for bit (same rescoring arithmetic)
+    ids2, scores2 = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["scan_fp32"])
+    np.testing.assert_array_equal(ids, ids2)
+    np.testing.assert_array_equal(scores, scores2)
+    fb = int(_cabi.lib().vs_fallback_count(st._handle))
+    assert fb <= B // 4, f"{fb} of {B} queries fell back to the exact scan"
+
+
+def test_gemm_auto_mode_and_uncertifiable_data(make_store):
+    """AUTO picks the GEMM path for large batches; on data with many near-ties (uniform rows:
+    all scores close together) certification fails for many queries and the exact fallback must
+    still return the oracle's answer."""
+    from b200vs import _cabi
+    n, d, B, k = 70000, 128, 96, 10
+    db = datasets.make_db(n, d, "uniform")
+    q = datasets.make_queries(B, d, "uniform")
+    st = make_store(d, "cosine")
+    st.add_vectors(db, [])
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "cosine")
+    ids, scores = st.search_arrays(q, k)          # auto
+    rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
+    assert rep.ok, f"{rep}"
+
+
+def test_gemm_duplicates_and_self_match(make_store):
+    from b200vs import _cabi
+    n, d, B, k = 70000, 128, 64, 10
+    db = datasets.make_db(n, d)
+    db[5] = db[2]
+    db[n - 1] = db[2]
+    q = datasets.make_queries(B, d)
+    q[0] = db[2]
+    q[1] = db[12345]
+    st = make_store(d, "cosine")
+    st.add_vectors(db, [])
+    ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["gemm"])
+    assert ids[0, :3].tolist() == [2, 5, n - 1]
+    assert ids[1, 0] == 12345 and scores[1, 0] > 0.9999
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "cosine")
+    rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
+    assert rep.ok, f"{rep}"

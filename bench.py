@@ -290,15 +290,19 @@ def run_b200(args):
                "clocks": clocks, "ids": ids, "scores": scores}
         n_local = n // world
         if gemm_n and gemm_ms >= scan_ms:
-            flops = 2.0 * B * n_local * d           # per launch: all B queries x local rows
-            per = gemm_ms / gemm_n
-            ach = flops / (per * 1e-3) / 1e12
-            peak = tc_sust if steps * (ms / steps) > 1000 else tc_burst
+            # K3 runs twice per step (sample pass + full pass): the algorithmic work of a step is
+            # 2*B*N_local*D flops, set against the summed duration of the step's GEMM launches
+            flops = 2.0 * B * n_local * d
+            per_step = gemm_ms / steps
+            ach = flops / (per_step * 1e-3) / 1e12
+            peak = tc_sust if ms > 1000 else tc_burst
             res["roofline"] = {"kernel": "gemm_topk (K3, tcgen05 bf16)", "bound": "tensor", "achieved": ach,
                                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                               "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16 cuBLAS",
-                               "launches": int(gemm_n), "avg_launch_ms": per,
-                               "kernel_share_of_step": gemm_ms / ms}
+                               "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16 cuBLAS "
+                                              f"({'sustained' if ms > 1000 else 'burst'})",
+                               "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
+                               "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
+                               "scan_fallback_ms_per_step": scan_ms / steps}
         elif scan_n:
             per = scan_ms / scan_n
             bytes_per_launch = float(n_local) * d * 4   # one pass over the fp32 rows of this shard

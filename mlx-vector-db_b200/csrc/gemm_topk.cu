@@ -120,6 +120,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
@@ -141,7 +147,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
 
 // -------------------------------------------------------------------- the kernel
 // MT > 0: RESIDENT with MT query tiles per CTA, TN = 128.  MT == 0: STREAMING, TN = 256.
-template <int MT>
+template <int MT, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p) {
@@ -283,103 +289,119 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue
+    // One thread owns one query row of the m-tile (TMEM lane = query).  Per accumulator the
+    // warp reads 32-column chunks (double-buffered tcgen05.ld) and reduces each to its
+    // maximum with 3-input FMNMX; only when some lane's maximum reaches its threshold does the
+    // warp take the rare path, which re-reads the chunk from TMEM 8 columns at a time (short
+    // code: the hot loop must stay resident in the instruction cache).
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;                   // query row inside the m-tile
     const int lists = RES ? ctas_in_group : (int)gridDim.x;
     const int list = RES ? cig : (int)blockIdx.x;
     const int64_t q_total = (int64_t)p.m_tiles * kTileM;
-    int cnt[RES ? MT : 1];
-    float tau[RES ? MT : 1];
-    if (RES) {
-#pragma unroll
-      for (int mt = 0; mt < (RES ? MT : 1); ++mt) {
-        cnt[mt] = 0;
+    (void)lists;
+    constexpr int NST = RES ? MT : 1;
+    float tau_l[NST];                                   // RESIDENT: per-thread state of its
+    int cnt_l[NST];                                     // query tiles (dynamically indexed)
+    if (RES && MODE == kModeFilter) {
+      for (int mt = 0; mt < NST; ++mt) {
+        cnt_l[mt] = 0;
         const int q = (m_first + mt) * kTileM + row;
-        tau[mt] = (p.mode == kModeFilter && q < p.nq) ? p.tau[q] : __int_as_float(0x7f800000);
+        tau_l[mt] = q < p.nq ? p.tau[q] : __int_as_float(0x7f800000);
       }
     }
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int nt = cig + i * ctas_in_group;
-#pragma unroll
-      for (int mtu = 0; mtu < (RES ? MT : 1); ++mtu) {
-        // RESIDENT: statically unrolled over the CTA's query tiles (state in registers);
-        // STREAMING: dynamic loop over all query tiles (state in global memory)
-        const int m_lo = RES ? mtu : 0;
-        const int m_hi = RES ? (mtu < m_count ? mtu + 1 : mtu) : m_count;
-        for (int mt = m_lo; mt < m_hi; ++mt, ++it) {
-          const int slot = it % SLOTS;
-          const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
-          const int q = (m_first + mt) * kTileM + row;
-          float t;
-          int c;
-          if (RES) { t = tau[mtu]; c = cnt[mtu]; }
-          else {
-            t = (p.mode == kModeFilter && q < p.nq) ? p.tau[q] : __int_as_float(0x7f800000);
-            c = p.mode == kModeFilter ? p.cand_cnt[(int64_t)list * q_total + q] : 0;
-          }
-          bar_wait(bar_accf + 8 * slot, aph);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
-          const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
-          float rmax = VS_NEG_INF;
 #pragma unroll 1
-          for (int c0 = 0; c0 < TN; c0 += 32) {
-            float v[32];
-            tc_ld32(taddr + (uint32_t)c0, v);
-            tc_wait_ld();
-            if (c0 + 32 == TN) {                        // accumulator fully read: hand it back
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) bar_arrive(bar_acce + 8 * slot);
+      for (int mt = 0; mt < m_count; ++mt, ++it) {
+        const int slot = it % SLOTS;
+        const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
+        const int q = (m_first + mt) * kTileM + row;
+        const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
+        float t = __int_as_float(0x7f800000);
+        int c = 0;
+        if (MODE == kModeFilter) {
+          if (RES) { t = tau_l[mt]; c = cnt_l[mt]; }
+          else {
+            if (q < p.nq) t = p.tau[q];
+            c = p.cand_cnt[(int64_t)list * q_total + q];
+          }
+        }
+        bar_wait(bar_accf + 8 * slot, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
+        float rmax = VS_NEG_INF;
+        float va[32], vb[32];
+        tc_ld32(taddr, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 64) {
+          tc_wait_ld();
+          tc_ld32(taddr + (uint32_t)(c0 + 32), vb);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float (&v)[32] = half == 0 ? va : vb;
+            const int cc = c0 + 32 * half;
+            if (half == 1) {
+              tc_wait_ld();
+              if (c0 + 64 < TN) tc_ld32(taddr + (uint32_t)(c0 + 64), va);
             }
-            if (p.mode == kModeDump) {
+            if (MODE == kModeDump) {
               if (q < p.nq) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  const int64_t r = (int64_t)nt * TN + c0 + j;
+                  const int64_t r = (int64_t)nt * TN + cc + j;
                   if (r < p.n_rows) p.dump[(int64_t)q * p.dump_ld + r] = v[j];
                 }
               }
-              continue;
-            }
-            float m01 = fmaxf(v[0], v[1]);
+            } else {
+              float m = fmaxf(v[0], v[1]);
 #pragma unroll
-            for (int j = 2; j < 32; j += 2) m01 = fmaxf(m01, fmaxf(v[j], v[j + 1]));
-            if (p.mode == kModeMax) { rmax = fmaxf(rmax, m01); continue; }
-            if (m01 >= t) {
-              const int64_t r0 = (int64_t)nt * TN + c0;
+              for (int j = 2; j < 32; j += 2) m = fmaxf(m, fmaxf(v[j], v[j + 1]));
+              if (MODE == kModeMax) rmax = fmaxf(rmax, m);
+              if (MODE == kModeFilter && __any_sync(0xffffffffu, m >= t)) {
+                // rare path (warp-uniform): re-read the chunk 8 columns at a time
+#pragma unroll 1
+                for (int g = 0; g < 32; g += 8) {
+                  float w[8];
+                  tc_ld8(taddr + (uint32_t)(cc + g), w);
+                  tc_wait_ld();
+                  const int64_t r0 = (int64_t)nt * TN + cc + g;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (v[j] >= t && r0 + j < p.n_rows) {
-                  if (c < kCandCap) {
-                    p.cand_score[cbase + c] = v[j];
-                    p.cand_id[cbase + c] = (int32_t)(r0 + j);
+                  for (int j = 0; j < 8; ++j) {
+                    if (w[j] >= t && r0 + j < p.n_rows) {
+                      if (c < kCandCap) {
+                        p.cand_score[cbase + c] = w[j];
+                        p.cand_id[cbase + c] = (int32_t)(r0 + j);
+                      }
+                      ++c;
+                    }
                   }
-                  ++c;
                 }
+                // the reload waited for every outstanding tcgen05.ld, including the prefetch
               }
             }
           }
-          if (p.mode == kModeMax && q < q_total) p.gmax[(int64_t)q * p.n_tiles + nt] = rmax;
-          if (RES) cnt[mtu] = c;
-          else if (p.mode == kModeFilter) p.cand_cnt[(int64_t)list * q_total + q] = c;
+        }
+        // accumulator fully consumed: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(bar_acce + 8 * slot);
+        if (MODE == kModeMax) p.gmax[(int64_t)q * p.n_tiles + nt] = rmax;
+        if (MODE == kModeFilter) {
+          if (RES) cnt_l[mt] = c;
+          else p.cand_cnt[(int64_t)list * q_total + q] = c;
         }
       }
     }
     // close the candidate lists: unused slots get id -1
-    if (p.mode == kModeFilter) {
-#pragma unroll
-      for (int mtu = 0; mtu < (RES ? MT : 1); ++mtu) {
-        const int m_lo = RES ? mtu : 0;
-        const int m_hi = RES ? (mtu < m_count ? mtu + 1 : mtu) : m_count;
-        for (int mt = m_lo; mt < m_hi; ++mt) {
-          const int q = (m_first + mt) * kTileM + row;
-          const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
-          int c = RES ? cnt[mtu] : p.cand_cnt[(int64_t)list * q_total + q];
-          if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }
-          for (int e = c; e < kCandCap; ++e) p.cand_id[cbase + e] = -1;
-        }
+    if (MODE == kModeFilter) {
+      for (int mt = 0; mt < m_count; ++mt) {
+        const int q = (m_first + mt) * kTileM + row;
+        const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
+        int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];
+        if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }
+        for (int e = c; e < kCandCap; ++e) p.cand_id[cbase + e] = -1;
       }
     }
   }
@@ -535,10 +557,10 @@ static bool plan_gemm(int kchunks, int m_tiles, GemmPlan* plan) {
   return true;
 }
 
-template <int MT>
-static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
-                         cudaStream_t stream) {
-  auto kern = gemm_topk_kernel<MT>;
+template <int MT, int MODE>
+static int launch_gemm_tm(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
+                          cudaStream_t stream) {
+  auto kern = gemm_topk_kernel<MT, MODE>;
   VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope prof(kProfGemm, stream);
@@ -547,6 +569,16 @@ static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const Gem
   count_launch();
   VS_CHECK_LAUNCH();
   return VS_OK;
+}
+
+template <int MT>
+static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
+                         cudaStream_t stream) {
+  switch (p.mode) {
+    case kModeFilter: return launch_gemm_tm<MT, kModeFilter>(mq, mx, p, grid, smem, stream);
+    case kModeMax: return launch_gemm_tm<MT, kModeMax>(mq, mx, p, grid, smem, stream);
+    default: return launch_gemm_tm<MT, kModeDump>(mq, mx, p, grid, smem, stream);
+  }
 }
 
 static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,

@@ -70,8 +70,11 @@ def test_tensor_core_scores_match_bf16_reference(make_store, shape, metric):
     # torch's fp32 normalisation can differ from the append kernel's by one ulp, which now and
     # then flips the bf16 rounding of one element (a 2^-8 relative step): tolerate a handful
     # of such entries, bounded by one bf16 ulp of one product
+    # (one flipped database element touches a whole column of scores, one flipped query element a
+    # whole row); dot_product has no normalisation, so there the match must be clean
     outliers = int((err > tol).sum())
-    assert outliers <= max(4, int(2e-5 * err.numel())), (outliers, float(err.max()))
+    allowed = 0 if metric == "dot_product" else max(4, int(1e-3 * err.numel()))
+    assert outliers <= allowed, (outliers, float(err.max()))
     assert float(err.max()) <= 2e-3 * scale, float(err.max())
 
 

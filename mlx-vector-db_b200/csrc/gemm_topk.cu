@@ -39,7 +39,7 @@
 
 namespace vs {
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kTileM = 128;              // queries per m-tile = TMEM lanes
 constexpr int kChunkK = 64;              // bf16 elements per 128-byte swizzled row
 constexpr int kChunkBytes = 128 * 128;   // 128 rows x 128 B
@@ -126,6 +126,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
@@ -295,6 +296,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // warp take the rare path, which re-reads the chunk from TMEM 8 columns at a time (short
     // code: the hot loop must stay resident in the instruction cache).
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+    const int grp = (warp - 4) >> 2;                    // warps 4-7 take even m-tiles, 8-11 odd ones
     const int row = quad * 32 + lane;                   // query row inside the m-tile
     const int lists = RES ? ctas_in_group : (int)gridDim.x;
     const int list = RES ? cig : (int)blockIdx.x;
@@ -315,6 +317,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int nt = cig + i * ctas_in_group;
 #pragma unroll 1
       for (int mt = 0; mt < m_count; ++mt, ++it) {
+        if ((mt & 1) != grp) continue;
         const int slot = it % SLOTS;
         const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
         const int q = (m_first + mt) * kTileM + row;
@@ -355,18 +358,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
               }
             } else {
-              float m = fmaxf(v[0], v[1]);
+              // maxima of the four 8-column groups (independent 3-input FMNMX trees)
+              float g[4];
 #pragma unroll
-              for (int j = 2; j < 32; j += 2) m = fmaxf(m, fmaxf(v[j], v[j + 1]));
+              for (int u = 0; u < 4; ++u) {
+                const float a = max3(v[8 * u], v[8 * u + 1], v[8 * u + 2]);
+                const float b = max3(v[8 * u + 3], v[8 * u + 4], v[8 * u + 5]);
+                g[u] = max3(a, b, fmaxf(v[8 * u + 6], v[8 * u + 7]));
+              }
+              const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
               if (MODE == kModeMax) rmax = fmaxf(rmax, m);
               if (MODE == kModeFilter && __any_sync(0xffffffffu, m >= t)) {
-                // rare path (warp-uniform): re-read the chunk 8 columns at a time
+                // rare path (warp-uniform): re-read only the 8-column groups that hold a hit
 #pragma unroll 1
-                for (int g = 0; g < 32; g += 8) {
+                for (int u = 0; u < 4; ++u) {
+                  const float gu = u == 0 ? g[0] : (u == 1 ? g[1] : (u == 2 ? g[2] : g[3]));
+                  if (!__any_sync(0xffffffffu, gu >= t)) continue;
                   float w[8];
-                  tc_ld8(taddr + (uint32_t)(cc + g), w);
+                  tc_ld8(taddr + (uint32_t)(cc + 8 * u), w);
                   tc_wait_ld();
-                  const int64_t r0 = (int64_t)nt * TN + cc + g;
+                  const int64_t r0 = (int64_t)nt * TN + cc + 8 * u;
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     if (w[j] >= t && r0 + j < p.n_rows) {
@@ -396,7 +407,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     // close the candidate lists: unused slots get id -1
     if (MODE == kModeFilter) {
-      for (int mt = 0; mt < m_count; ++mt) {
+      for (int mt = grp; mt < m_count; mt += 2) {        // this warp group's query tiles
         const int q = (m_first + mt) * kTileM + row;
         const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];

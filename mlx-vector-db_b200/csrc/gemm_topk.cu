@@ -28,6 +28,7 @@
 //   STREAMING (any K): query and database chunks both stream through the ring per 64-wide K
 //     step; database tiles of 256 rows; 2 TMEM accumulators of 256 columns.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -57,7 +58,9 @@ struct GemmParams {
   int ngroups;              // RESIDENT: query groups (CTA c serves group c % ngroups)
   int nq;                   // live queries
   int mode;
+  int fp16;                 // operands are fp16 (cosine) instead of bf16
   int stages;               // ring depth
+  uint32_t idesc;           // tcgen05 instruction descriptor (operand format, M, N)
   const float* tau;         // (nq,) filter threshold (kModeFilter)
   float* cand_score;        // (lists, m_tiles*128, kCandCap)
   int32_t* cand_id;
@@ -141,9 +144,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major
-__host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, both operands K-major,
+// operand format 0 = fp16, 1 = bf16
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
 // -------------------------------------------------------------------- the kernel
@@ -242,7 +247,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (lane == 0 && my_tiles > 0 && m_count > 0) {
-      constexpr uint32_t idesc = instr_desc(kTileM, TN);
+      const uint32_t idesc = p.idesc;
       if (RES) bar_wait(bar_a, 0);
       int st = 0;
       uint32_t ph = 0;
@@ -447,9 +452,17 @@ __global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int
   for (int c = lane; c < ld16; c += 32) {
     float v = c < dim ? src[c] : 0.f;
     if (metric == VS_METRIC_COSINE) v = v / nrm;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    dst[c] = h;
-    const float d = v - __bfloat162float(h);
+    float vb;
+    if (metric == VS_METRIC_COSINE) {     // fp16 operands for unit-norm data, bf16 otherwise
+      const __half h = __float2half_rn(v);
+      reinterpret_cast<__half*>(dst)[c] = h;
+      vb = __half2float(h);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      dst[c] = h;
+      vb = __bfloat162float(h);
+    }
+    const float d = v - vb;
     e2 = fmaf(d, d, e2);
     u2 = fmaf(v, v, u2);
   }
@@ -529,14 +542,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 // (rows, K) bf16 row-major matrix, boxes of 128 rows x 64 elements, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K) {
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, bool fp16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VS_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {(cuuint32_t)kChunkK, 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return VS_ERR_CUDA; }
@@ -595,6 +608,7 @@ static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const Gem
 static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,
                        int num_sms, int* lists_out, cudaStream_t stream) {
   p.stages = plan.stages;
+  p.idesc = instr_desc(kTileM, plan.tn, p.fp16 ? 0 : 1);
   int grid = num_sms;
   if (plan.mt > 0) {
     p.ngroups = (p.m_tiles + plan.mt - 1) / plan.mt;
@@ -697,8 +711,9 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   if (int rc = ws.alloc(stream)) return rc;
 
   CUtensorMap mq, mx;
-  if (int rc = make_map(&mq, qb, rows_padded, K)) return rc;
-  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K)) return rc;
+  const bool fp16 = s->metric == VS_METRIC_COSINE;
+  if (int rc = make_map(&mq, qb, rows_padded, K, fp16)) return rc;
+  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16)) return rc;
 
   prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
                                                                     qerr, qlen);
@@ -708,7 +723,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   VS_CUDA(cudaMemsetAsync(nbad, 0, 4, stream));
 
   GemmParams p = {};
-  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B;
+  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = fp16 ? 1 : 0;
   p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
   if (plan.mt == 0) VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
   if (sampled) {
@@ -815,14 +830,15 @@ int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, 
   ws.want(&qlen, (size_t)rows_padded);
   if (int rc = ws.alloc(stream)) return rc;
   CUtensorMap mq, mx;
-  if (int rc = make_map(&mq, qb, rows_padded, K)) return rc;
-  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K)) return rc;
+  const bool fp16 = s->metric == VS_METRIC_COSINE;
+  if (int rc = make_map(&mq, qb, rows_padded, K, fp16)) return rc;
+  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16)) return rc;
   prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
                                                                     qerr, qlen);
   count_launch();
   VS_CHECK_LAUNCH();
   GemmParams p = {};
-  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B;
+  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = fp16 ? 1 : 0;
   p.mode = kModeDump; p.n_tiles = (int)((n + plan.tn - 1) / plan.tn); p.dump = out; p.dump_ld = ld;
   return launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream);
 }

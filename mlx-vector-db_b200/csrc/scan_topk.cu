@@ -8,6 +8,7 @@
 // that can no longer enter the global top-k.  Row r is skipped iff key < tau, so ties at the
 // threshold survive and the final (key desc, id asc) order is deterministic.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "scan_topk.cuh"
 
 namespace vs {
@@ -112,11 +113,12 @@ template <> struct Log2<1> { static constexpr int value = 0; };
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <bool L2, bool BF16>
+// FMT: 0 = fp32 rows, 1 = bf16 shadow rows, 2 = fp16 shadow rows (cosine: unit-norm rows)
+template <bool L2, int FMT>
 struct Acc;  // accumulate one 16-byte database vector against the query
 
 template <bool L2>
-struct Acc<L2, false> {
+struct Acc<L2, 0> {
   using Vec = float4;
   static constexpr int kQPerVec = 1;  // float4 query vectors per database vector
   __device__ static __forceinline__ Vec load_global(const void* base, int64_t idx) {
@@ -128,8 +130,28 @@ struct Acc<L2, false> {
     return L2 ? sqdiff4_acc(acc, x, qv) : dot4_acc(acc, x, qv);
   }
 };
+__device__ __forceinline__ float2 h2f(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
 template <bool L2>
-struct Acc<L2, true> {
+struct Acc<L2, 2> {
+  using Vec = uint4;
+  __device__ static __forceinline__ Vec load_global(const void* base, int64_t idx) {
+    return ldg_stream_u4(reinterpret_cast<const uint4*>(base) + idx);
+  }
+  __device__ static __forceinline__ float run(float acc, const Vec& x, const float4* q, int c,
+                                              int plane_stride) {
+    const float4 q0 = q[c];
+    const float4 q1 = q[plane_stride + c];
+    const float2 a = h2f(x.x), b = h2f(x.y), cc = h2f(x.z), d = h2f(x.w);
+    const float4 x0 = make_float4(a.x, a.y, b.x, b.y);
+    const float4 x1 = make_float4(cc.x, cc.y, d.x, d.y);
+    acc = L2 ? sqdiff4_acc(acc, x0, q0) : dot4_acc(acc, x0, q0);
+    return L2 ? sqdiff4_acc(acc, x1, q1) : dot4_acc(acc, x1, q1);
+  }
+};
+template <bool L2>
+struct Acc<L2, 1> {
   using Vec = uint4;
   __device__ static __forceinline__ Vec load_global(const void* base, int64_t idx) {
     return ldg_stream_u4(reinterpret_cast<const uint4*>(base) + idx);
@@ -246,11 +268,11 @@ __device__ __forceinline__ bool mask_bit(const uint32_t* mask, int64_t row) {
 }
 
 // ------------------------------------------------------------ LDG variant
-template <int QB, int R, bool L2, bool BF16>
+template <int QB, int R, bool L2, int FMT>
 __global__ void __launch_bounds__(kMaxScanWarps * 32)
 scan_topk_ldg_kernel(const ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  using A = Acc<L2, BF16>;
+  using A = Acc<L2, FMT>;
   constexpr int V = QB * R;
   constexpr int SH = 5 - Log2<V>::value;
   const ScanSmem s = carve(smem, QB, p.ldq, p.k, p.warps);
@@ -307,11 +329,11 @@ scan_topk_ldg_kernel(const ScanParams p) {
 // Warp p.warps is the producer; warps 0..p.warps-1 consume.  Ring of p.stages tiles of
 // p.tile_rows rows (+ their clamped norms for fp32 cosine, a second bulk copy on the same
 // barrier); full[s] (count 1 + tx bytes) / empty[s] (count p.warps) mbarriers.
-template <int QB, int R, bool L2, bool BF16>
+template <int QB, int R, bool L2, int FMT>
 __global__ void __launch_bounds__((kMaxTmaWarps + 1) * 32, 1)
 scan_topk_tma_kernel(const ScanParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  using A = Acc<L2, BF16>;
+  using A = Acc<L2, FMT>;
   constexpr int V = QB * R;
   constexpr int SH = 5 - Log2<V>::value;
   const int nwarps = p.warps;
@@ -422,12 +444,12 @@ static int env_int(const char* name, int dflt) {
   return e && *e ? atoi(e) : dflt;
 }
 
-template <int QB, int R, bool L2, bool BF16>
+template <int QB, int R, bool L2, int FMT>
 static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, bool dry_run,
                       cudaStream_t stream) {
   const size_t fixed = scan_fixed_smem(QB, p.ldq, p.k, p.warps);
   if (!use_tma) {
-    auto kern = scan_topk_ldg_kernel<QB, R, L2, BF16>;
+    auto kern = scan_topk_ldg_kernel<QB, R, L2, FMT>;
     const size_t smem = fixed;
     if (smem > 48 * 1024)
       VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -451,7 +473,7 @@ static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, 
     VS_CHECK_LAUNCH();
     return VS_OK;
   }
-  auto kern = scan_topk_tma_kernel<QB, R, L2, BF16>;
+  auto kern = scan_topk_tma_kernel<QB, R, L2, FMT>;
   const bool stage_norms = p.epilogue == VS_METRIC_COSINE && p.norms != nullptr;
   const size_t smem = fixed + 128 +
                       (size_t)p.stages * ((size_t)p.tile_rows * p.vec_per_row * 16 + (stage_norms ? p.tile_rows * 4 : 0));
@@ -470,34 +492,34 @@ static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, 
   return VS_OK;
 }
 
-template <int QB, bool L2, bool BF16>
+template <int QB, bool L2, int FMT>
 static int launch_r(const ScanParams& p, int r, bool use_tma, int num_sms, int* nl, bool dry,
                     cudaStream_t st) {
   switch (r) {
-    case 1: return launch_one<QB, 1, L2, BF16>(p, use_tma, num_sms, nl, dry, st);
-    case 2: return launch_one<QB, 2, L2, BF16>(p, use_tma, num_sms, nl, dry, st);
-    case 4: if constexpr (QB <= 4) return launch_one<QB, 4, L2, BF16>(p, use_tma, num_sms, nl, dry, st); break;
-    case 8: if constexpr (QB <= 2) return launch_one<QB, 8, L2, BF16>(p, use_tma, num_sms, nl, dry, st); break;
-    case 16: if constexpr (QB == 1) return launch_one<QB, 16, L2, BF16>(p, use_tma, num_sms, nl, dry, st); break;
+    case 1: return launch_one<QB, 1, L2, FMT>(p, use_tma, num_sms, nl, dry, st);
+    case 2: return launch_one<QB, 2, L2, FMT>(p, use_tma, num_sms, nl, dry, st);
+    case 4: if constexpr (QB <= 4) return launch_one<QB, 4, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
+    case 8: if constexpr (QB <= 2) return launch_one<QB, 8, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
+    case 16: if constexpr (QB == 1) return launch_one<QB, 16, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
   }
   set_error("internal: unsupported rows-per-warp");
   return VS_ERR_INVALID;
 }
 
-template <bool L2, bool BF16>
+template <bool L2, int FMT>
 static int launch_qb(const ScanParams& p, int qb, int r, bool use_tma, int num_sms, int* nl,
                      bool dry, cudaStream_t st) {
   switch (qb) {
-    case 1: return launch_r<1, L2, BF16>(p, r, use_tma, num_sms, nl, dry, st);
-    case 2: return launch_r<2, L2, BF16>(p, r, use_tma, num_sms, nl, dry, st);
-    case 4: return launch_r<4, L2, BF16>(p, r, use_tma, num_sms, nl, dry, st);
-    case 8: return launch_r<8, L2, BF16>(p, r, use_tma, num_sms, nl, dry, st);
+    case 1: return launch_r<1, L2, FMT>(p, r, use_tma, num_sms, nl, dry, st);
+    case 2: return launch_r<2, L2, FMT>(p, r, use_tma, num_sms, nl, dry, st);
+    case 4: return launch_r<4, L2, FMT>(p, r, use_tma, num_sms, nl, dry, st);
+    case 8: return launch_r<8, L2, FMT>(p, r, use_tma, num_sms, nl, dry, st);
   }
   set_error("internal: unsupported query block");
   return VS_ERR_INVALID;
 }
 
-int launch_scan(const ScanParams& base, int qb, bool l2, bool bf16, bool use_tma, int num_sms,
+int launch_scan(const ScanParams& base, int qb, bool l2, int fmt, bool use_tma, int num_sms,
                 int* nlists_out, size_t* part_elems_out, bool dry_run, cudaStream_t stream) {
   ScanParams p = base;
   // consumer warps: 12 while the per-warp lists stay small, else 8
@@ -525,10 +547,11 @@ int launch_scan(const ScanParams& base, int qb, bool l2, bool bf16, bool use_tma
     p.stages = stages;
   }
   int rc;
-  if (l2) rc = bf16 ? launch_qb<true, true>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream)
-                    : launch_qb<true, false>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream);
-  else    rc = bf16 ? launch_qb<false, true>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream)
-                    : launch_qb<false, false>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream);
+  if (l2) rc = fmt ? launch_qb<true, 1>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream)
+                   : launch_qb<true, 0>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream);
+  else if (fmt == 2) rc = launch_qb<false, 2>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream);
+  else rc = fmt ? launch_qb<false, 1>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream)
+                : launch_qb<false, 0>(p, qb, r, use_tma, num_sms, nlists_out, dry_run, stream);
   if (rc == VS_OK && part_elems_out) *part_elems_out = (size_t)qb * (*nlists_out) * p.k;
   return rc;
 }

@@ -18,7 +18,7 @@ inline int scan_warps_for(int qb, int k) {
 }
 
 struct ScanParams {
-  const void* db;          // fp32 rows (vec = 4 floats) or bf16 rows (vec = 8 bf16), 16 B vectors
+  const void* db;          // fp32 rows (vec = 4 floats) or 16-bit shadow rows (vec = 8), 16 B vectors
   int64_t n;               // rows visible to this search
   int vec_per_row;         // 16-byte vectors per row
   const float* norms;      // max(||x||,1e-8) per row (fp32 cosine only)
@@ -40,7 +40,7 @@ struct ScanParams {
 
 // host launcher: scans `db` for queries [0, nb) of the prepared block and leaves
 // per-warp lists + tau behind; returns the number of lists per query via *nlists.
-int launch_scan(const ScanParams& base, int qb, bool l2, bool bf16, bool use_tma, int num_sms,
+int launch_scan(const ScanParams& base, int qb, bool l2, int fmt, bool use_tma, int num_sms,
                 int* nlists_out, size_t* part_elems_out, bool dry_run, cudaStream_t stream);
 
 // prepare queries: cosine -> q / max(||q||, 1e-8); pad to ldq; bf16 database -> split into

@@ -64,6 +64,8 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
   p.n = n;
   p.vec_per_row = bf16 ? s->ld16 / 8 : s->ld / 4;
   const bool l2 = s->metric == VS_METRIC_EUCLIDEAN;
+  // 16-bit shadow: fp16 for cosine (unit-norm rows), bf16 otherwise (store.cu, K1)
+  const int fmt = !bf16 ? 0 : (s->metric == VS_METRIC_COSINE ? 2 : 1);
   // the cosine bf16 shadow is stored normalised: its epilogue is a plain dot product
   p.epilogue = (bf16 && s->metric == VS_METRIC_COSINE) ? VS_METRIC_DOT : s->metric;
   p.norms = (!bf16 && s->metric == VS_METRIC_COSINE) ? (const float*)s->norms.ptr() : nullptr;
@@ -76,7 +78,7 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
   for (int qb = 1; qb <= qb_max; qb <<= 1) {
     int nl = 0; size_t pe = 0;
     p.nb = qb;
-    if (int rc = launch_scan(p, qb, l2, bf16, use_tma, s->num_sms, &nl, &pe, true, stream)) return rc;
+    if (int rc = launch_scan(p, qb, l2, fmt, use_tma, s->num_sms, &nl, &pe, true, stream)) return rc;
     if (pe > part_elems) part_elems = pe;
   }
   Workspace ws;
@@ -98,7 +100,7 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
     p.nb = nb;
     p.tau = tau + b0;
     int nl = 0;
-    if (int rc = launch_scan(p, qb, l2, bf16, use_tma, s->num_sms, &nl, nullptr, false, stream)) return rc;
+    if (int rc = launch_scan(p, qb, l2, fmt, use_tma, s->num_sms, &nl, nullptr, false, stream)) return rc;
     if (int rc = launch_merge(part_key, part_id, (int64_t)nl * kk, nb, kk, tau + b0, l2 ? 1 : 0,
                               out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride,
                               out_stride, stream, map_ids ? s->id_map() : nullptr, kk))

@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda_fp16.h>
 #include "store.cuh"
 
 namespace vs {
@@ -231,9 +232,18 @@ append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restr
       for (int c = lane; c < ld16; c += 32) {
         float v = c < dim ? s[c] : 0.f;
         if (normalize_shadow) v = v / nrm;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        sh[c] = h;
-        const float vb = __bfloat162float(h);
+        // cosine: unit-norm rows fit fp16's range and keep 11 significant bits (8x smaller
+        // rounding error than bf16 -> far tighter certification); raw rows keep bf16's range
+        float vb;
+        if (normalize_shadow) {
+          const __half h = __float2half_rn(v);
+          reinterpret_cast<__half*>(sh)[c] = h;
+          vb = __half2float(h);
+        } else {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          sh[c] = h;
+          vb = __bfloat162float(h);
+        }
         const float dlt = v - vb;
         e2 = fmaf(dlt, dlt, e2);
         s2 = fmaf(vb, vb, s2);

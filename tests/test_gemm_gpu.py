@@ -25,8 +25,10 @@ def _bf16_reference(q, db, metric):
     if metric == "cosine":
         qd = qd / qd.norm(dim=1, keepdim=True).clamp_min(1e-8)
         xd = xd / xd.norm(dim=1, keepdim=True).clamp_min(1e-8)
-    qb = qd.to(torch.bfloat16).to(torch.float32)
-    xb = xd.to(torch.bfloat16).to(torch.float32)
+    # 16-bit operand format of the engine: fp16 for cosine (unit-norm rows), bf16 otherwise
+    half = torch.float16 if metric == "cosine" else torch.bfloat16
+    qb = qd.to(half).to(torch.float32)
+    xb = xd.to(half).to(torch.float32)
     return (qb.double() @ xb.double().T).float()
 
 
@@ -75,7 +77,7 @@ def test_tensor_core_scores_match_bf16_reference(make_store, shape, metric):
     outliers = int((err > tol).sum())
     allowed = 0 if metric == "dot_product" else max(4, int(1e-3 * err.numel()))
     assert outliers <= allowed, (outliers, float(err.max()))
-    assert float(err.max()) <= 2e-3 * scale, float(err.max())
+    assert float(err.max()) <= (3e-4 if metric == "cosine" else 2e-3 * scale), float(err.max())
 
 
 SEARCH_SHAPES = [

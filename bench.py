@@ -282,6 +282,8 @@ def run_b200(args):
         barrier()
         clocks = sampler.stop() if rank == 0 else {}
         ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.vs_launch_count() - launches0
+        lib.vs_profile(0)
         if ms < 700.0:
             # the timed region was too short for nvidia-smi's 100 ms sampling: keep the same step
             # running (untimed, every rank -- the all-gather is collective) and sample under load
@@ -296,8 +298,6 @@ def run_b200(args):
             if rank == 0:
                 clocks = sampler.stop()
                 clocks["sampled"] = f"under the same load right after the timed region ({extra} extra steps)"
-        launches = lib.vs_launch_count() - launches0
-        lib.vs_profile(0)
         scan_ms, scan_n = read_profile(0)
         gemm_ms, gemm_n = read_profile(1)
         res = {"ms_per_step": ms / steps, "qps": B * steps / (ms / 1e3), "launches": int(launches),

@@ -152,20 +152,92 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, int fmt) {
 }
 
 // -------------------------------------------------------------------- the kernel
-// MT > 0: RESIDENT with MT query tiles per CTA, TN = 128.  MT == 0: STREAMING, TN = 256.
-template <int MT, int MODE>
+// MT > 0: RESIDENT with MT query tiles per CTA.  MT == 0: STREAMING.
+// CG = 1: one CTA per MMA (M = 128).  CG = 2: a CTA pair (cluster of 2, `cta_group::2`) shares
+// every MMA: M = 256 = 128 query rows from each CTA, N = 256 database rows of which each CTA
+// loads and holds half; the leader (cluster rank 0) issues the MMAs for both, accumulator rows
+// land in each CTA's own TMEM.  Halves the shared-memory operand reads per MMA and the
+// database bytes each SM pulls through TMA.
+//   MMA N (database rows per tile) TN: RESIDENT CG=1: 128, otherwise 256.
+template <int CG> struct CgOps;
+template <> struct CgOps<1> {
+  __device__ static __forceinline__ void alloc(uint32_t dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  __device__ static __forceinline__ void dealloc(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmemCols) : "memory");
+  }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    tc_mma(d, a, b, idesc, acc);
+  }
+  __device__ static __forceinline__ void commit(uint32_t bar) { tc_commit(bar); }
+  __device__ static __forceinline__ void load(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    tma_load_2d(dst, map, c0, c1, bar);
+  }
+};
+template <> struct CgOps<2> {
+  __device__ static __forceinline__ void alloc(uint32_t dst) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  __device__ static __forceinline__ void dealloc(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmemCols) : "memory");
+  }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  }
+  // arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair
+  __device__ static __forceinline__ void commit(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+  }
+  // the transaction bytes are credited to the LEADER's barrier (peer bit of the address cleared)
+  __device__ static __forceinline__ void load(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+  }
+};
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void bar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+
+template <int MT, int MODE, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p) {
   constexpr bool RES = MT > 0;
-  constexpr int TN = RES ? 128 : 256;
+  constexpr int TN = (RES && CG == 1) ? 128 : 256;        // MMA N = database rows per tile
+  constexpr int TN_LOCAL = TN / CG;                       // rows of the tile this CTA loads
   constexpr int SLOTS = kTmemCols / TN;
-  constexpr int B_CHUNK_BYTES = TN * 128;
+  constexpr int B_CHUNK_BYTES = TN_LOCAL * 128;
+  using Ops = CgOps<CG>;
   extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment for the 128B-swizzle atoms
+  // 1024-byte alignment for the 128B-swizzle atoms (same offset in both CTAs of a pair)
   unsigned char* smem = smem_raw + ((1024 - (s_u32(smem_raw) & 1023)) & 1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kch = p.kchunks;
+  const int crank = CG == 2 ? (int)cluster_rank() : 0;    // 0 = leader (issues the MMAs)
 
   // ---- carve-up
   unsigned char* a_res = smem;                                         // RES: MT*kch chunks
@@ -182,73 +254,79 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t bar_acce = s_u32(bars + 1 + 2 * p.stages + SLOTS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * p.stages + 2 * SLOTS);
 
-  // ---- work assignment
+  // ---- work assignment, in units of one CTA (CG=1) or one CTA pair (CG=2)
+  // query tiles are counted per unit: unit tile m covers the 128-row tiles m*CG + crank
+  const int unit = blockIdx.x / CG;
+  const int n_units = gridDim.x / CG;
+  const int um_tiles = p.m_tiles / CG;                                 // m_tiles is a multiple of CG
   const int ngroups = RES ? p.ngroups : 1;
-  const int group = blockIdx.x % ngroups;
-  const int cig = blockIdx.x / ngroups;                                // CTA index inside its group
-  const int ctas_in_group = (gridDim.x - group + ngroups - 1) / ngroups;
+  const int group = unit % ngroups;
+  const int uig = unit / ngroups;                                      // unit index inside its group
+  const int units_in_group = (n_units - group + ngroups - 1) / ngroups;
   const int m_first = RES ? group * MT : 0;
-  const int m_count = RES ? min(MT, p.m_tiles - m_first) : p.m_tiles;
+  const int m_count = RES ? min(MT, um_tiles - m_first) : um_tiles;
   int my_tiles = 0;
-  if (cig < p.n_tiles) my_tiles = (p.n_tiles - cig + ctas_in_group - 1) / ctas_in_group;
+  if (uig < p.n_tiles) my_tiles = (p.n_tiles - uig + units_in_group - 1) / units_in_group;
 
   if (threadIdx.x == 0) {
     bar_init(bar_a, 1);
     for (int i = 0; i < p.stages; ++i) { bar_init(bar_full + 8 * i, 1); bar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < SLOTS; ++i) { bar_init(bar_accf + 8 * i, 1); bar_init(bar_acce + 8 * i, 4); }
+    for (int i = 0; i < SLOTS; ++i) { bar_init(bar_accf + 8 * i, 1); bar_init(bar_acce + 8 * i, 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
-                 "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 2) Ops::alloc(s_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // both CTAs' barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================================================================ TMA producer
+    // Every CTA loads its own operands; with CG = 2 the bytes of both CTAs are credited to the
+    // leader's full barriers, which the leader arms with the pair's total.
     if (lane == 0 && my_tiles > 0 && m_count > 0) {
       if (RES) {
-        bar_expect_tx(bar_a, (uint32_t)(m_count * kch * kChunkBytes));
+        if (crank == 0) bar_expect_tx(bar_a, (uint32_t)(CG * m_count * kch * kChunkBytes));
         for (int mt = 0; mt < m_count; ++mt)
           for (int kc = 0; kc < kch; ++kc)
-            tma_load_2d(s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes), &map_q, kc * kChunkK,
-                        (m_first + mt) * kTileM, bar_a);
+            Ops::load(s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes), &map_q, kc * kChunkK,
+                      ((m_first + mt) * CG + crank) * kTileM, bar_a);
       }
       int st = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int nt = cig + i * ctas_in_group;
+        const int nt = uig + i * units_in_group;
+        const int row0 = nt * TN + crank * TN_LOCAL;                  // first database row this CTA loads
         if (RES) {
           bar_wait(bar_empty + 8 * st, ph ^ 1u);
-          bar_expect_tx(bar_full + 8 * st, (uint32_t)(kch * B_CHUNK_BYTES));
-          for (int kc = 0; kc < kch; ++kc)
-            tma_load_2d(s_u32(ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES), &map_x,
-                        kc * kChunkK, nt * TN, bar_full + 8 * st);
+          if (crank == 0) bar_expect_tx(bar_full + 8 * st, (uint32_t)(CG * kch * B_CHUNK_BYTES));
+          for (int kc = 0; kc < kch; ++kc) {
+            unsigned char* dst = ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES;
+            Ops::load(s_u32(dst), &map_x, kc * kChunkK, row0, bar_full + 8 * st);
+            if (TN_LOCAL == 256) Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kChunkK, row0 + 128, bar_full + 8 * st);
+          }
           if (++st == p.stages) { st = 0; ph ^= 1u; }
         } else {
           for (int mt = 0; mt < m_count; ++mt)
             for (int kc = 0; kc < kch; ++kc) {
               bar_wait(bar_empty + 8 * st, ph ^ 1u);
-              bar_expect_tx(bar_full + 8 * st, (uint32_t)(kChunkBytes + B_CHUNK_BYTES));
+              if (crank == 0) bar_expect_tx(bar_full + 8 * st, (uint32_t)(CG * (kChunkBytes + B_CHUNK_BYTES)));
               unsigned char* dst = ring + (size_t)st * stage_bytes;
-              tma_load_2d(s_u32(dst), &map_q, kc * kChunkK, mt * kTileM, bar_full + 8 * st);
-              // database tile of 256 rows = two boxes of 128 rows
-              tma_load_2d(s_u32(dst + kChunkBytes), &map_x, kc * kChunkK, nt * TN, bar_full + 8 * st);
-              tma_load_2d(s_u32(dst + 2 * kChunkBytes), &map_x, kc * kChunkK, nt * TN + 128, bar_full + 8 * st);
+              Ops::load(s_u32(dst), &map_q, kc * kChunkK, (mt * CG + crank) * kTileM, bar_full + 8 * st);
+              Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kChunkK, row0, bar_full + 8 * st);
+              if (TN_LOCAL == 256)   // 256 rows = two boxes of 128
+                Ops::load(s_u32(dst + 2 * kChunkBytes), &map_x, kc * kChunkK, row0 + 128, bar_full + 8 * st);
               if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0 && my_tiles > 0 && m_count > 0) {
+    // ================================================================ MMA issuer (leader CTA)
+    if (lane == 0 && crank == 0 && my_tiles > 0 && m_count > 0) {
       const uint32_t idesc = p.idesc;
-      if (RES) bar_wait(bar_a, 0);
+      if (RES) { bar_wait(bar_a, 0); tc_fence_after(); }
       int st = 0;
       uint32_t ph = 0;
       int it = 0;                                       // (n-tile, m-tile) sequence number
@@ -260,7 +338,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int mt = 0; mt < m_count; ++mt, ++it) {
           const int slot = it % SLOTS;
           const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
-          bar_wait(bar_acce + 8 * slot, aph ^ 1u);      // epilogue drained this accumulator
+          bar_wait(bar_acce + 8 * slot, aph ^ 1u);      // epilogues drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TN);
           for (int kc = 0; kc < kch; ++kc) {
@@ -278,17 +356,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint64_t b_desc = smem_desc(b_addr);
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k)      // +32 B per 16-element K step
-              tc_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                     (kc | k) != 0 ? 1u : 0u);
+              Ops::mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                       (kc | k) != 0 ? 1u : 0u);
             if (!RES) {
-              tc_commit(bar_empty + 8 * st);            // smem stage free once these MMAs retire
+              Ops::commit(bar_empty + 8 * st);          // smem stage free once these MMAs retire
               if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
           }
-          tc_commit(bar_accf + 8 * slot);               // accumulator ready for the epilogue
+          Ops::commit(bar_accf + 8 * slot);             // accumulator ready for the epilogues
         }
         if (RES) {
-          tc_commit(bar_empty + 8 * st);
+          Ops::commit(bar_empty + 8 * st);
           if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
       }
@@ -298,34 +376,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // One thread owns one query row of the m-tile (TMEM lane = query).  Per accumulator the
     // warp reads 32-column chunks (double-buffered tcgen05.ld) and reduces each to its
     // maximum with 3-input FMNMX; only when some lane's maximum reaches its threshold does the
-    // warp take the rare path, which re-reads the chunk from TMEM 8 columns at a time (short
+    // warp take the rare path, which re-reads the offending 8-column groups from TMEM (short
     // code: the hot loop must stay resident in the instruction cache).
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const int grp = (warp - 4) >> 2;                    // warps 4-7 take even m-tiles, 8-11 odd ones
     const int row = quad * 32 + lane;                   // query row inside the m-tile
-    const int lists = RES ? ctas_in_group : (int)gridDim.x;
-    const int list = RES ? cig : (int)blockIdx.x;
+    const int list = RES ? uig : unit;                  // candidate list of this unit
     const int64_t q_total = (int64_t)p.m_tiles * kTileM;
-    (void)lists;
     constexpr int NST = RES ? MT : 1;
     float tau_l[NST];                                   // RESIDENT: per-thread state of its
     int cnt_l[NST];                                     // query tiles (dynamically indexed)
     if (RES && MODE == kModeFilter) {
       for (int mt = 0; mt < NST; ++mt) {
         cnt_l[mt] = 0;
-        const int q = (m_first + mt) * kTileM + row;
+        const int q = ((m_first + mt) * CG + crank) * kTileM + row;
         tau_l[mt] = q < p.nq ? p.tau[q] : __int_as_float(0x7f800000);
       }
     }
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int nt = cig + i * ctas_in_group;
+      const int nt = uig + i * units_in_group;
 #pragma unroll 1
       for (int mt = 0; mt < m_count; ++mt, ++it) {
         if ((mt & 1) != grp) continue;
         const int slot = it % SLOTS;
         const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
-        const int q = (m_first + mt) * kTileM + row;
+        const int q = ((m_first + mt) * CG + crank) * kTileM + row;
         const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         float t = __int_as_float(0x7f800000);
         int c = 0;
@@ -399,10 +475,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
           }
         }
-        // accumulator fully consumed: hand it back to the MMA warp
+        // accumulator fully consumed: hand it back to the (leader's) MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) bar_arrive(bar_acce + 8 * slot);
+        if (lane == 0) {
+          if (CG == 2 && crank != 0) bar_arrive_remote(bar_acce + 8 * slot, 0);
+          else bar_arrive(bar_acce + 8 * slot);
+        }
         if (MODE == kModeMax) p.gmax[(int64_t)q * p.n_tiles + nt] = rmax;
         if (MODE == kModeFilter) {
           if (RES) cnt_l[mt] = c;
@@ -413,7 +492,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // close the candidate lists: unused slots get id -1
     if (MODE == kModeFilter) {
       for (int mt = grp; mt < m_count; mt += 2) {        // this warp group's query tiles
-        const int q = (m_first + mt) * kTileM + row;
+        const int q = ((m_first + mt) * CG + crank) * kTileM + row;
         const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];
         if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }
@@ -424,9 +503,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // the peer's smem / TMEM stay alive until the leader is done
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    Ops::dealloc(tmem_base);
   }
 }
 
@@ -557,75 +637,111 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, boo
 }
 
 struct GemmPlan {
-  int mt;            // resident query tiles per CTA (0 = streaming)
+  int mt;            // resident query tiles per unit (0 = streaming)
+  int cg;            // CTAs per MMA: 1, or 2 (CTA pairs, cta_group::2)
   int stages;
   size_t smem;
-  int tn;
+  int tn;            // database rows per tile (MMA N)
 };
 
-static bool plan_gemm(int kchunks, int m_tiles, GemmPlan* plan) {
-  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/;
-  if (kchunks <= 4) {   // K <= 256: resident queries
-    int mt = kchunks <= 2 ? 4 : 1;
-    if (mt > m_tiles) mt = m_tiles >= 2 ? 2 : 1;
-    const size_t a = (size_t)mt * kchunks * kChunkBytes;
-    const size_t stage = (size_t)kchunks * kChunkBytes;
-    int stages = (int)((limit - a) / stage);
-    if (stages > 4) stages = 4;
-    if (stages >= 2) { *plan = {mt, stages, a + stages * stage + 1024 + 512, 128}; return true; }
-  }
-  const size_t stage = (size_t)3 * kChunkBytes;   // query chunk + 256-row database chunk
-  int stages = (int)(limit / stage);
-  if (stages > 6) stages = 6;
-  *plan = {0, stages, stages * stage + 1024 + 512, 256};
-  return true;
+// CTAs per MMA.  Measured on B200: CTA pairs win where the kernel streams both
+// operands (K > 256: +9 % at D = 768, +67 % at D = 1536); with resident queries (K <= 256) the
+// bound is the TMEM read-out of the epilogue, and four 128-column accumulators per CTA (cg = 1)
+// pipeline it better than two 256-column ones.  B200VS_GEMM_CG=1|2 forces one.
+static int gemm_cta_group(int kchunks) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("B200VS_GEMM_CG"); forced = e && *e ? atoi(e) : 0; }
+  if (forced == 1 || forced == 2) return forced;
+  return kchunks <= 4 ? 1 : 2;
 }
 
-template <int MT, int MODE>
-static int launch_gemm_tm(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
-                          cudaStream_t stream) {
-  auto kern = gemm_topk_kernel<MT, MODE>;
+// m_tiles: 128-row query tiles, already a multiple of cg
+static void plan_gemm(int kchunks, int m_tiles, int cg, GemmPlan* plan) {
+  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/;
+  const int um_tiles = m_tiles / cg;
+  if (kchunks <= 4) {   // K <= 256: resident queries
+    int mt = kchunks <= 2 ? 4 : 1;
+    while (mt > um_tiles) mt >>= 1;
+    if (mt < 1) mt = 1;
+    const size_t a = (size_t)mt * kchunks * kChunkBytes;
+    const size_t stage = (size_t)kchunks * kChunkBytes;          // 128 database rows per CTA
+    int stages = (int)((limit - a) / stage);
+    if (stages > 4) stages = 4;
+    if (stages >= 2) { *plan = {mt, cg, stages, a + stages * stage + 1024 + 512, cg == 2 ? 256 : 128}; return; }
+  }
+  // streaming: query chunk + this CTA's share of the 256-row database chunk
+  const size_t stage = (size_t)(cg == 2 ? 2 : 3) * kChunkBytes;
+  int stages = (int)(limit / stage);
+  if (stages > 6) stages = 6;
+  *plan = {0, cg, stages, stages * stage + 1024 + 512, 256};
+}
+
+template <int MT, int MODE, int CG>
+static int launch_gemm_tmc(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
+                           cudaStream_t stream) {
+  auto kern = gemm_topk_kernel<MT, MODE, CG>;
   VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   {
     ProfScope prof(kProfGemm, stream);
-    kern<<<grid, kGemmThreads, smem, stream>>>(mq, mx, p);
+    VS_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, p));
   }
   count_launch();
   VS_CHECK_LAUNCH();
   return VS_OK;
 }
 
+template <int MT, int MODE>
+static int launch_gemm_tm(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int cg, int grid,
+                          size_t smem, cudaStream_t stream) {
+  return cg == 2 ? launch_gemm_tmc<MT, MODE, 2>(mq, mx, p, grid, smem, stream)
+                 : launch_gemm_tmc<MT, MODE, 1>(mq, mx, p, grid, smem, stream);
+}
+
 template <int MT>
-static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
-                         cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int cg, int grid,
+                         size_t smem, cudaStream_t stream) {
   switch (p.mode) {
-    case kModeFilter: return launch_gemm_tm<MT, kModeFilter>(mq, mx, p, grid, smem, stream);
-    case kModeMax: return launch_gemm_tm<MT, kModeMax>(mq, mx, p, grid, smem, stream);
-    default: return launch_gemm_tm<MT, kModeDump>(mq, mx, p, grid, smem, stream);
+    case kModeFilter: return launch_gemm_tm<MT, kModeFilter>(mq, mx, p, cg, grid, smem, stream);
+    case kModeMax: return launch_gemm_tm<MT, kModeMax>(mq, mx, p, cg, grid, smem, stream);
+    default: return launch_gemm_tm<MT, kModeDump>(mq, mx, p, cg, grid, smem, stream);
   }
 }
 
 static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,
                        int num_sms, int* lists_out, cudaStream_t stream) {
   p.stages = plan.stages;
-  p.idesc = instr_desc(kTileM, plan.tn, p.fp16 ? 0 : 1);
-  int grid = num_sms;
+  p.idesc = instr_desc(kTileM * plan.cg, plan.tn, p.fp16 ? 0 : 1);
+  int units = num_sms / plan.cg;                       // CTAs (cg = 1) or CTA pairs (cg = 2)
   if (plan.mt > 0) {
-    p.ngroups = (p.m_tiles + plan.mt - 1) / plan.mt;
+    const int um_tiles = p.m_tiles / plan.cg;
+    p.ngroups = (um_tiles + plan.mt - 1) / plan.mt;
     const int64_t want = (int64_t)p.n_tiles * p.ngroups;
-    if (want < grid) grid = (int)want;
-    if (grid < p.ngroups) grid = p.ngroups;
-    if (lists_out) *lists_out = (grid + p.ngroups - 1) / p.ngroups;
+    if (want < units) units = (int)want;
+    if (units < p.ngroups) units = p.ngroups;
+    if (lists_out) *lists_out = (units + p.ngroups - 1) / p.ngroups;
   } else {
     p.ngroups = 1;
-    if (p.n_tiles < grid) grid = p.n_tiles;
-    if (lists_out) *lists_out = grid;
+    if (p.n_tiles < units) units = p.n_tiles;
+    if (lists_out) *lists_out = units;
   }
+  const int grid = units * plan.cg;
   switch (plan.mt) {
-    case 0: return launch_gemm_t<0>(mq, mx, p, grid, plan.smem, stream);
-    case 1: return launch_gemm_t<1>(mq, mx, p, grid, plan.smem, stream);
-    case 2: return launch_gemm_t<2>(mq, mx, p, grid, plan.smem, stream);
-    case 4: return launch_gemm_t<4>(mq, mx, p, grid, plan.smem, stream);
+    case 0: return launch_gemm_t<0>(mq, mx, p, plan.cg, grid, plan.smem, stream);
+    case 1: return launch_gemm_t<1>(mq, mx, p, plan.cg, grid, plan.smem, stream);
+    case 2: return launch_gemm_t<2>(mq, mx, p, plan.cg, grid, plan.smem, stream);
+    case 4: return launch_gemm_t<4>(mq, mx, p, plan.cg, grid, plan.smem, stream);
   }
   set_error("internal: bad GEMM plan");
   return VS_ERR_INVALID;
@@ -679,11 +795,12 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
                       float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
   const int K = s->ld16;
   const int kch = K / kChunkK;
-  const int m_tiles = (B + kTileM - 1) / kTileM;
+  const int cg = gemm_cta_group(kch);
+  const int m_tiles = ((B + kTileM * cg - 1) / (kTileM * cg)) * cg;     // a multiple of cg
   const int rows_padded = m_tiles * kTileM;
   const int kc = (int)std::min<int64_t>(cand_count(kk), n);
   GemmPlan plan;
-  plan_gemm(kch, m_tiles, &plan);
+  plan_gemm(kch, m_tiles, cg, &plan);
   const int tn = plan.tn;
   const int n_tiles = (int)((n + tn - 1) / tn);
   // pass-1 sample: about 1/16 of the rows, at most 4096 tiles (merge kernel capacity), whole tiles
@@ -819,10 +936,11 @@ int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certif
 int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, int64_t ld, cudaStream_t stream) {
   const int K = s->ld16;
   const int kch = K / kChunkK;
-  const int m_tiles = (B + kTileM - 1) / kTileM;
+  const int cg = gemm_cta_group(kch);
+  const int m_tiles = ((B + kTileM * cg - 1) / (kTileM * cg)) * cg;
   const int rows_padded = m_tiles * kTileM;
   GemmPlan plan;
-  plan_gemm(kch, m_tiles, &plan);
+  plan_gemm(kch, m_tiles, cg, &plan);
   Ws ws;
   __nv_bfloat16* qb; float *qerr, *qlen;
   ws.want(&qb, (size_t)rows_padded * K);

@@ -112,11 +112,20 @@ merge_topk_kernel(const MergeParams p) {
     }
   }
   __syncthreads();
-  for (int64_t i = tid; i < p.per_query; i += kMergeThreads) {
-    float key; int id;
-    if (cand_load(p, b, i, thr, key, id)) {
-      const int pos = atomicAdd(&cnt, 1);
-      if (pos < kMergeCap) { sk[pos] = key; si[pos] = id; }
+  // compaction with one shared-memory atomic per warp (ballot + prefix popcount)
+  for (int64_t i0 = 0; i0 < p.per_query; i0 += kMergeThreads) {
+    const int64_t i = i0 + tid;
+    float key = 0.f; int id = 0;
+    const bool ok = i < p.per_query && cand_load(p, b, i, thr, key, id);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (bal) {
+      int base = 0;
+      if ((tid & 31) == 0) base = atomicAdd(&cnt, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ok) {
+        const int pos = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+        if (pos < kMergeCap) { sk[pos] = key; si[pos] = id; }
+      }
     }
   }
   __syncthreads();

@@ -33,6 +33,7 @@ WORKLOADS = {          # name -> (rows, dim)
     "1Mx768": (1_000_000, 768),
     "5Mx384": (5_000_000, 384),
     "100Kx384": (100_000, 384),
+    "1.25Mx128": (1_250_000, 128),   # one shard of the 8-GPU headline run (diagnostic)
 }
 N_BLOCKS = 8           # the database is generated in 8 seeded blocks so every N in {1,2,4,8} sees the same rows
 DB_SEED, QUERY_SEED = 1234, 4321
@@ -203,6 +204,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner to stdout; the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from b200vs import _cabi, build

@@ -31,6 +31,7 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -803,8 +804,15 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   plan_gemm(kch, m_tiles, cg, &plan);
   const int tn = plan.tn;
   const int n_tiles = (int)((n + tn - 1) / tn);
-  // pass-1 sample: about 1/16 of the rows, at most 4096 tiles (merge kernel capacity), whole tiles
-  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>(n / 16 / tn, 4 * kc), 4096);
+  // pass-1 sample size.  Pass 1 costs ~0.8 f of a full pass (f = sampled fraction); pass 2 then
+  // sees about kc / f survivors per query, i.e. a fraction 1024 kc / (f N) of its 32x32 chunks
+  // take the rare path (~1.5 chunk times each).  Minimising 0.8 f + 1536 kc / (f N) gives
+  // f = sqrt(1920 kc / N): 8 % at N = 10 M, 22 % at N = 1.25 M (one of 8 shards).  At most 4096
+  // tiles (merge kernel capacity), at least 4 kc, whole tiles only.
+  double f = std::sqrt(1920.0 * kc / (double)n);
+  if (f > 0.5) f = 0.5;
+  if (f < 1.0 / 32) f = 1.0 / 32;
+  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, 4 * kc), 4096);
   if (s_tiles > (int)(n / tn)) s_tiles = (int)(n / tn);
   const bool sampled = s_tiles >= 2 * kc;
 

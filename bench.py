@@ -188,6 +188,95 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- extra configs (N = 1)
+def config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args):
+    """BASELINE config C: 1M x 1536 L2 top-100, bf16 database scan + fp32 rescoring of the
+    candidates; recall@100 against the engine's own exact fp32 scan (itself oracle-checked in
+    tests/) and throughput at batch 1 and 16."""
+    import torch
+    n, d, k = 1_000_000, 1536, 100
+    out = {"workload": "1Mx1536 L2 top-100, bf16 database + fp32 rescoring (config C)"}
+    exact = ShardedVectorStore(d, "euclidean", device=dev, shadow_bf16=True, max_vectors_per_shard=n + 16,
+                               search_mode="scan_fp32")
+    for b in range(N_BLOCKS):
+        g = torch.Generator(device=dev).manual_seed(DB_SEED + b)
+        rows = torch.randn((n // N_BLOCKS, d), generator=g, device=dev, dtype=torch.float32)
+        exact.shard.append(rows, b * (n // N_BLOCKS))
+        del rows
+    exact.total = n
+    q = torch.randn((16, d), generator=torch.Generator().manual_seed(QUERY_SEED), dtype=torch.float32).to(dev)
+    ref_ids, _ = exact.search(q, k)
+    exact.shard.flags = _cabi.SEARCH_MODES["scan_bf16"]        # same store, 16-bit scan + K5
+    got_ids, _ = exact.search(q, k)
+    ref = ref_ids.cpu().numpy()
+    got = got_ids.cpu().numpy()
+    hits = sum(len(set(r.tolist()) & set(g_.tolist())) for r, g_ in zip(ref, got))
+    out["recall_at_100_vs_exact_fp32"] = hits / ref.size
+    for B in (1, 16):
+        qq = q[:B].contiguous()
+        for _ in range(3):
+            exact.search(qq, k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 20
+        e0.record()
+        for _ in range(steps):
+            exact.search(qq, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[f"batch{B}_qps"] = B / (ms * 1e-3)
+        out[f"batch{B}_ms_per_step"] = ms
+        out[f"batch{B}_scan_gbs_of_bf16_bytes"] = n * d * 2 / (ms * 1e-3) / 1e9
+    exact.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def config_e_streaming(dev, lib, _cabi, ShardedVectorStore, args):
+    """BASELINE config E: 5M x 384 mixed streaming workload -- the store starts at 1M rows and
+    grows to 5M by 10 000-row appends (K1, in-place arena growth), each followed by a batch-256
+    top-10 query against everything appended so far."""
+    import torch
+    d, k, B, step_rows, n0, n1 = 384, 10, 256, 10_000, 1_000_000, 5_000_000
+    st = ShardedVectorStore(d, "cosine", device=dev, shadow_bf16=True, max_vectors_per_shard=n1 + 16,
+                            search_mode=args.mode)
+    g = torch.Generator(device=dev).manual_seed(DB_SEED)
+    first = torch.randn((n0, d), generator=g, device=dev, dtype=torch.float32)
+    st.add_vectors(first)
+    del first
+    q = torch.randn((B, d), generator=torch.Generator().manual_seed(QUERY_SEED), dtype=torch.float32).to(dev)
+    chunk = torch.randn((step_rows, d), generator=g, device=dev, dtype=torch.float32)
+    st.search(q, k)
+    torch.cuda.synchronize()
+    cycles = (n1 - n0) // step_rows
+    fb0 = int(lib.vs_fallback_count(st.shard.handle))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for c in range(cycles):
+        chunk.add_(0.001)                      # new rows every cycle (cheap, on device)
+        st.add_vectors(chunk)
+        ids, scores = st.search(q, k)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    # the last appended chunk must be searchable: its first row finds itself
+    probe_ids, probe_scores = st.search(chunk[:1].contiguous(), 1)
+    ok = int(probe_ids[0, 0].item()) == st.total - step_rows and float(probe_scores[0, 0].item()) > 0.9999
+    out = {"workload": "5Mx384 streaming: 1M -> 5M rows by 10k-row appends, each followed by a batch-256 "
+                       "top-10 query (config E)",
+           "cycles": cycles, "total_ms": ms, "wall_ms": wall * 1e3, "ms_per_cycle": ms / cycles,
+           "query_qps_during_ingest": B * cycles / (ms * 1e-3),
+           "append_rows_per_s_during_queries": step_rows * cycles / (ms * 1e-3),
+           "final_rows": st.total, "last_chunk_searchable": ok,
+           "exact_fallbacks": int(lib.vs_fallback_count(st.shard.handle)) - fb0}
+    st.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import numpy as np
@@ -393,6 +482,8 @@ def run_b200(args):
             st2.close()
             del st2
             torch.cuda.empty_cache()
+        extras.append(config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args))
+        extras.append(config_e_streaming(dev, lib, _cabi, ShardedVectorStore, args))
     else:
         st.close()
 

@@ -552,33 +552,105 @@ __global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int
   if (lane == 0) { qerr[b] = sqrtf(e2) * 1.00001f; qlen[b] = sqrtf(u2) * 1.00001f; }
 }
 
-// certification + compaction of the queries that need the exact fallback
-__global__ void certify_kernel(int B, int k, int kc, int64_t n_rows, const float* __restrict__ cand_s,
-                               const int32_t* __restrict__ cand_i, const float* __restrict__ tau,
-                               const int32_t* __restrict__ overflow, const float* __restrict__ out_s,
-                               const int32_t* __restrict__ out_i, int64_t out_stride,
-                               const float* __restrict__ qerr, const float* __restrict__ qlen,
-                               const uint32_t* __restrict__ bounds, float slack, int* __restrict__ n_bad,
-                               int32_t* __restrict__ bad_list) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float max_err = __uint_as_float(bounds[0]);
-  const float max_len = __uint_as_float(bounds[1]);
-  // |exact - bf16| <= ||u|| * max||v - v^|| + ||u - u^|| * max||v^|| (+ fp32 accumulation slack)
-  const float E = qlen[b] * max_err + qerr[b] * max_len + slack * (1.f + qlen[b] * max_len);
-  // bf16 score no row outside the candidate set can exceed
-  const bool full = cand_i[(int64_t)b * kc + kc - 1] >= 0;
-  const float beta = full ? cand_s[(int64_t)b * kc + kc - 1] : tau[b];
-  const int kk = (int)(n_rows < k ? n_rows : k);
-  bool ok = overflow[b] == 0;
-  if (ok) {
-    if (!full && n_rows <= kc) ok = true;              // every row is a candidate
-    else {
-      const bool have_k = out_i[(int64_t)b * out_stride + kk - 1] >= 0;
-      ok = have_k && out_s[(int64_t)b * out_stride + kk - 1] > beta + E;
+// K5 + final K4 + certification in one launch: one CTA per query.
+//   warp 0 prepares the query exactly like prep_queries_kernel (so the scores below are bit-
+//   identical to K2's), the 8 warps rescore the kc candidates in exact fp32 with K2's
+//   accumulation order, warp 0 orders them by (key desc, id asc), writes the top k and decides
+//   whether the candidate set provably contains the exact top-k:
+//       |exact - 16bit| <= ||u|| * max||v - v^|| + ||u - u^|| * max||v^|| + slack =: E
+//       certified  <=>  exact k-th  >  beta + E,   beta = 16-bit score no outside row exceeds
+constexpr int kFinishThreads = 256;
+constexpr int kMaxCand = 64;
+
+struct FinishParams {
+  const float* q;            // (B, dim) raw queries
+  int dim, ld, metric, B, k, kc;
+  int64_t n_rows;
+  const float* rows;         // (n, ld) fp32 master
+  const float* norms;
+  const int32_t* id_map;     // nullable
+  const float* cand_s;       // (B, kc) 16-bit scores, best first
+  const int32_t* cand_i;     // (B, kc) local ids, -1 = empty
+  const float* tau;
+  const int32_t* overflow;
+  const float* qerr;
+  const float* qlen;
+  const uint32_t* bounds;
+  float slack;
+  int certify;
+  float* out_s;
+  int32_t* out_i;
+  int64_t out_stride;
+  int* n_bad;
+  int32_t* bad_list;
+};
+
+__global__ void __launch_bounds__(kFinishThreads)
+finish_kernel(const FinishParams p) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  float4* qs = reinterpret_cast<float4*>(fsm);                 // prepared query, ld floats
+  __shared__ float keys[kMaxCand];
+  __shared__ int ids[kMaxCand];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = p.q + (size_t)b * p.dim;
+  if (warp == 0) {
+    float acc = 0.f;
+    for (int c = lane; c < p.dim; c += 32) { const float v = src[c]; acc = fmaf(v, v, acc); }
+    const float nrm = fmaxf(sqrtf(warp_sum(acc)), 1e-8f);
+    float* dst = reinterpret_cast<float*>(qs);
+    for (int c = lane; c < p.ld; c += 32) {
+      float v = c < p.dim ? src[c] : 0.f;
+      dst[c] = p.metric == VS_METRIC_COSINE ? v / nrm : v * 1.f;
     }
   }
-  if (!ok) bad_list[atomicAdd(n_bad, 1)] = b;
+  __syncthreads();
+  const int nvec = p.ld >> 2;
+  for (int e = warp; e < p.kc; e += kFinishThreads / 32) {
+    const int id = p.cand_i[(int64_t)b * p.kc + e];
+    float key = VS_NEG_INF;
+    if (id >= 0) {
+      const float4* x = reinterpret_cast<const float4*>(p.rows) + (int64_t)id * nvec;
+      float acc = 0.f;
+      for (int c = lane; c < nvec; c += 32) acc = dot4_acc(acc, ldg_stream(x + c), qs[c]);
+      const float tot = warp_sum(acc);
+      key = p.metric == VS_METRIC_COSINE ? tot / __ldg(p.norms + id) : tot;
+    }
+    if (lane == 0) { keys[e] = key; ids[e] = id < 0 ? VS_ID_SENTINEL : (p.id_map ? p.id_map[id] : id); }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  // rank by counting: lane handles candidates lane and lane + 32
+  float* os = p.out_s + (int64_t)b * p.out_stride;
+  int32_t* oi = p.out_i + (int64_t)b * p.out_stride;
+  const int kk = (int)(p.n_rows < p.k ? p.n_rows : p.k);
+  float kth = VS_NEG_INF;
+  int have = 0;
+  for (int e = lane; e < p.kc; e += 32) {
+    const float mk = keys[e];
+    const int mi = ids[e];
+    if (mi == VS_ID_SENTINEL) continue;
+    int r = 0;
+    for (int j = 0; j < p.kc; ++j) r += (ids[j] != VS_ID_SENTINEL) && better(keys[j], ids[j], mk, mi);
+    if (r < p.k) { os[r] = mk; oi[r] = mi; }
+    if (r == kk - 1) { kth = mk; have = 1; }
+  }
+  int valid = 0;
+  for (int e = lane; e < p.kc; e += 32) valid += ids[e] != VS_ID_SENTINEL;
+  for (int off = 16; off; off >>= 1) {
+    valid += __shfl_xor_sync(0xffffffffu, valid, off);
+    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
+    have |= __shfl_xor_sync(0xffffffffu, have, off);
+  }
+  for (int e = (valid < p.k ? valid : p.k) + lane; e < p.out_stride; e += 32) { os[e] = 0.f; oi[e] = -1; }
+  if (lane != 0 || !p.certify) return;
+  const float max_err = __uint_as_float(p.bounds[0]);
+  const float max_len = __uint_as_float(p.bounds[1]);
+  const float E = p.qlen[b] * max_err + p.qerr[b] * max_len + p.slack * (1.f + p.qlen[b] * max_len);
+  const bool full = p.cand_i[(int64_t)b * p.kc + p.kc - 1] >= 0;
+  const float beta = full ? p.cand_s[(int64_t)b * p.kc + p.kc - 1] : p.tau[b];
+  bool ok = p.overflow[b] == 0;
+  if (ok && !(!full && p.n_rows <= p.kc)) ok = have && kth > beta + E;
+  if (!ok) p.bad_list[atomicAdd(p.n_bad, 1)] = b;
 }
 
 __global__ void fill_f32_kernel(float* p, float v, int64_t n) {
@@ -765,7 +837,7 @@ static int cand_count(int kk) { return std::max(2 * kk, kk + 22); }
 bool gemm_supported(const vs_store* s, int64_t n, int B, int kk) {
   if (!gemm_enabled() || !s->shadow) return false;
   if (s->metric == VS_METRIC_EUCLIDEAN) return false;       // L2 candidates: bf16 scan path
-  if (B < gemm_min_batch()) return false;
+  if (B < gemm_min_batch() || s->dim > 8192) return false;
   if (cand_count(kk) > 64) return false;
   if (n < 65536) return false;                              // small stores: the scan is enough
   return true;
@@ -859,10 +931,8 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
     MergeParams m = {};
     m.ck = gmax; m.ci = nullptr; m.per_query = s_tiles; m.chunk = s_tiles; m.chunk_stride = 0;
     m.query_stride = s_tiles; m.list_len = 0; m.k = kc; m.tau = nullptr;
-    m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
+    m.out_s = c1s; m.out_i = c1i; m.out_stride = kc; m.kth_out = tau;      // tau[b] = kc-th largest
     if (int rc = launch_merge(m, B, stream)) return rc;
-    // tau[b] = c1s[b][kc-1]
-    VS_CUDA(cudaMemcpy2DAsync(tau, 4, c1s + (kc - 1), (size_t)kc * 4, 4, B, cudaMemcpyDeviceToDevice, stream));
   } else {
     // tiny store: no sample, every row is a candidate of the filter (tau = -inf)
     fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, -__builtin_inff(), rows_padded);
@@ -881,24 +951,19 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
     m.k = kc; m.tau = nullptr; m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
     if (int rc = launch_merge(m, B, stream)) return rc;
   }
-  // K5: exact fp32 scores of the candidates, then the final top-k
+  // K5 + final K4 + certification, one CTA per query
   {
-    float* qprep = nullptr;
-    VS_CUDA(cudaMallocAsync((void**)&qprep, (size_t)B * s->ld * 4, stream));
-    int rc = launch_prep_queries(q, B, s->dim, s->metric, s->ld, false, 1.f, qprep, nullptr, nullptr, stream);
-    if (!rc) rc = launch_rescore((const float*)s->rows.ptr(), s->ld, s->dim, (const float*)s->norms.ptr(), s->metric,
-                                 qprep, s->ld, B, c1i, kc, rk, stream);
-    if (!rc) rc = launch_merge(rk, c1i, kc, B, kk, nullptr, 0, out_scores, out_ids, out_stride, stream, s->id_map());
-    cudaFreeAsync(qprep, stream);
-    if (rc) return rc;
+    FinishParams f = {};
+    f.q = q; f.dim = s->dim; f.ld = s->ld; f.metric = s->metric; f.B = B; f.k = kk; f.kc = kc; f.n_rows = n;
+    f.rows = (const float*)s->rows.ptr(); f.norms = (const float*)s->norms.ptr(); f.id_map = s->id_map();
+    f.cand_s = c1s; f.cand_i = c1i; f.tau = tau; f.overflow = ovf; f.qerr = qerr; f.qlen = qlen;
+    f.bounds = s->bounds; f.slack = 4.f * (float)s->dim * 5.9604645e-8f + 1e-6f; f.certify = certify ? 1 : 0;
+    f.out_s = out_scores; f.out_i = out_ids; f.out_stride = out_stride; f.n_bad = nbad; f.bad_list = bad;
+    finish_kernel<<<B, kFinishThreads, (size_t)s->ld * 4, stream>>>(f);
+    count_launch();
+    VS_CHECK_LAUNCH();
   }
   if (!certify) return VS_OK;
-  // certification needs LOCAL row ids only through their validity (>= 0), so the id map does not matter
-  const float slack = 4.f * (float)s->dim * 5.9604645e-8f + 1e-6f;
-  certify_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, kk, kc, n, c1s, c1i, tau, ovf, out_scores, out_ids,
-                                                     out_stride, qerr, qlen, s->bounds, slack, nbad, bad);
-  count_launch();
-  VS_CHECK_LAUNCH();
   int h_bad = 0;
   VS_CUDA(cudaMemcpyAsync(&h_bad, nbad, 4, cudaMemcpyDeviceToHost, stream));
   VS_CUDA(cudaStreamSynchronize(stream));

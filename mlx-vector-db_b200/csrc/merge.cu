@@ -210,6 +210,7 @@ merge_topk_kernel(const MergeParams p) {
       int r = 0;
       for (int j = 0; j < n; ++j) r += better(sk[j], si[j], mk, mi);
       if (r < k) { os[r] = p.negate_out ? -mk : mk; oi[r] = mi; }
+      if (r == k - 1 && p.kth_out) p.kth_out[b] = mk;
     }
     written = n < k ? n : k;
   } else if (n <= kMergeCap) {
@@ -222,6 +223,7 @@ merge_topk_kernel(const MergeParams p) {
     for (int i = tid; i < written; i += kMergeThreads) {
       os[i] = p.negate_out ? -sk[i] : sk[i];
       oi[i] = si[i];
+      if (i == k - 1 && p.kth_out) p.kth_out[b] = sk[i];
     }
   } else {
     // selection passes: next = best candidate strictly worse than the previous pick
@@ -249,12 +251,16 @@ merge_topk_kernel(const MergeParams p) {
         if (better(red_k[w], red_i[w], bk, bi)) { bk = red_k[w]; bi = red_i[w]; }
       __syncthreads();
       if (bi == VS_ID_SENTINEL) break;
-      if (tid == 0) { os[j] = p.negate_out ? -bk : bk; oi[j] = bi; }
+      if (tid == 0) {
+        os[j] = p.negate_out ? -bk : bk; oi[j] = bi;
+        if (j == k - 1 && p.kth_out) p.kth_out[b] = bk;
+      }
       last_k = bk; last_i = bi;
       written = j + 1;
     }
   }
   for (int64_t i = written + tid; i < p.out_stride; i += kMergeThreads) { os[i] = 0.f; oi[i] = -1; }
+  if (written < k && tid == 0 && p.kth_out) p.kth_out[b] = VS_NEG_INF;   // fewer than k candidates
 }
 
 int launch_merge(const MergeParams& p, int B, cudaStream_t stream) {

@@ -69,6 +69,7 @@ struct MergeParams {
   float* out_s;
   int32_t* out_i;
   int64_t out_stride;
+  float* kth_out;          // nullable: (B,) the k-th best key (-inf when fewer than k candidates)
 };
 int launch_merge(const MergeParams& p, int B, cudaStream_t stream);
 // scan-list layout: candidates of query b contiguous at b * per_query

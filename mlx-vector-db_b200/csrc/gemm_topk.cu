@@ -827,7 +827,10 @@ static int gemm_enabled() {
 }
 static int gemm_min_batch() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("B200VS_GEMM_MIN_BATCH"); v = e && *e ? atoi(e) : 48; }
+  // measured on B200 (10M x 128): K3 takes 0.53-0.58 ms for any batch of 8..64 queries (it is
+  // HBM-bound on the 16-bit shadow there), K2 needs 0.88 ms for one query and ~4 ms per pass of
+  // 8 -- so everything but single queries goes to K3
+  if (v < 0) { const char* e = getenv("B200VS_GEMM_MIN_BATCH"); v = e && *e ? atoi(e) : 2; }
   return v;
 }
 

@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--mode", default="auto")
+    ap.add_argument("--dist", default="normal", choices=["normal", "uniform"],
+                    help="row / query distribution: N(0,1) or the reference tests' np.random.rand U[0,1)")
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE shapes/batches (default: on at N=1)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
@@ -340,7 +342,10 @@ def run_b200(args):
                 continue
             g = torch.Generator(device=dev).manual_seed(DB_SEED + b)
             # same stream on any N: block b is always generated whole with its own seed
-            rows = torch.randn((per_block, d), generator=g, device=dev, dtype=torch.float32)
+            if args.dist == "uniform":
+                rows = torch.rand((per_block, d), generator=g, device=dev, dtype=torch.float32)
+            else:
+                rows = torch.randn((per_block, d), generator=g, device=dev, dtype=torch.float32)
             st.shard.append(rows, b * per_block)
             del rows
         st.total = per_block * N_BLOCKS
@@ -354,8 +359,13 @@ def run_b200(args):
 
     def measure(st, n, d, B, k, steps, warmup, with_e2e=True):
         gq = torch.Generator().manual_seed(QUERY_SEED)
-        q_host = torch.randn((B, d), generator=gq, dtype=torch.float32).pin_memory()
+        if args.dist == "uniform":
+            q_host = torch.rand((B, d), generator=gq, dtype=torch.float32).pin_memory()
+        else:
+            q_host = torch.randn((B, d), generator=gq, dtype=torch.float32).pin_memory()
         q_dev = q_host.to(dev)
+        fb0 = int(lib.vs_fallback_count(st.shard.handle))
+        rt0 = int(lib.vs_retry_count(st.shard.handle))
         for _ in range(warmup):
             ids, scores = st.search(q_dev, k)
         # ---- device-resident timing (value) ----
@@ -393,6 +403,10 @@ def run_b200(args):
         scan_ms, scan_n = read_profile(0)
         gemm_ms, gemm_n = read_profile(1)
         res = {"ms_per_step": ms / steps, "qps": B * steps / (ms / 1e3), "launches": int(launches),
+               "exact_fallback_queries_per_step": (int(lib.vs_fallback_count(st.shard.handle)) - fb0) /
+                                                  max(1, warmup + steps + (extra if ms < 700.0 else 0)),
+               "wide_retry_queries_per_step": (int(lib.vs_retry_count(st.shard.handle)) - rt0) /
+                                              max(1, warmup + steps + (extra if ms < 700.0 else 0)),
                "clocks": clocks, "ids": ids, "scores": scores}
         n_local = n // world
         if gemm_n and gemm_ms >= scan_ms:
@@ -526,10 +540,13 @@ def run_b200(args):
                        "batch": B, "k": k, "sharding": f"rows/{world}", "search_mode": args.mode,
                        "l2_policy": "database (5.1 GB fp32 + 2.6 GB bf16) is far larger than the 126 MB L2; "
                                     "no flush needed between steps",
-                       "data_detail": "N(0,1) rows, 8 seeded blocks (seed 1234+b), queries seed 4321",
+                       "data_detail": f"{'U[0,1)' if args.dist == 'uniform' else 'N(0,1)'} rows, 8 seeded blocks "
+                                      f"(seed 1234+b), queries seed 4321",
                        "result_checksum": checksum},
             "e2e": main.get("e2e"),
             "gpu_launches": main["launches"],
+            "exact_fallback_queries_per_step": main["exact_fallback_queries_per_step"],
+            "wide_retry_queries_per_step": main["wide_retry_queries_per_step"],
             "clocks": main["clocks"],
             "roofline": main.get("roofline"),
             "cpu_baseline": cpu_baseline,

@@ -138,6 +138,9 @@ VS_API int vs_search_host(vs_store* s, const float* q_host, int B, int k, int fl
  * folded into the result (uncertified queries are re-run exactly); this returns how many
  * queries took the exact fallback in total since creation (diagnostic). */
 VS_API int64_t vs_fallback_count(const vs_store* s);
+/* Queries the GEMM path could not certify with its default candidate count and retried once
+ * with four times as many before (if still uncertified) falling back (diagnostic). */
+VS_API int64_t vs_retry_count(const vs_store* s);
 
 /* K4 merge_topk -- new (the reference is single-device): merge G candidate lists of k
  * entries per query into (B, k).  Group g's (B, k) block starts at g * group_stride elements

@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         "vs_search": (i32, [p, f32p, i32, i32, i32, u32p, f32p, i32p, p]),
         "vs_search_host": (i32, [p, f32p, i32, i32, i32, u32p, f32p, i32p]),
         "vs_fallback_count": (i64, [p]),
+        "vs_retry_count": (i64, [p]),
         "vs_merge": (i32, [i32, i32, f32p, i32p, i32, i32, i32, i64, f32p, i32p, p]),
         "vs_rescore": (i32, [p, f32p, i32, i32p, i32, i32, f32p, i32p, p]),
         "vs_debug_gemm_scores": (i32, [p, f32p, i32, f32p, p]),

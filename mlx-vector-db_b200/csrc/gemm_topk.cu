@@ -560,7 +560,7 @@ __global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int
 //       |exact - 16bit| <= ||u|| * max||v - v^|| + ||u - u^|| * max||v^|| + slack =: E
 //       certified  <=>  exact k-th  >  beta + E,   beta = 16-bit score no outside row exceeds
 constexpr int kFinishThreads = 256;
-constexpr int kMaxCand = 64;
+constexpr int kMaxCand = 256;
 
 struct FinishParams {
   const float* q;            // (B, dim) raw queries
@@ -628,7 +628,7 @@ finish_kernel(const FinishParams p) {
   for (int e = lane; e < p.kc; e += 32) {
     const float mk = keys[e];
     const int mi = ids[e];
-    if (mi == VS_ID_SENTINEL) continue;
+    if (mi == VS_ID_SENTINEL) continue;   // (kc <= kMaxCand, checked by the host)
     int r = 0;
     for (int j = 0; j < p.kc; ++j) r += (ids[j] != VS_ID_SENTINEL) && better(keys[j], ids[j], mk, mi);
     if (r < p.k) { os[r] = mk; oi[r] = mi; }
@@ -867,14 +867,17 @@ struct Ws {
 int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, float* out_scores,
                        int32_t* out_ids, int64_t out_stride, cudaStream_t stream);
 
+// kc_want: candidates kept for rescoring (0 = default for kk); a query that cannot be certified
+// is retried once with 4x the candidates (a wider bf16 margin) before the exact scan takes it
 static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
-                      float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
+                      float* out_scores, int32_t* out_ids, int64_t out_stride, int kc_want,
+                      cudaStream_t stream) {
   const int K = s->ld16;
   const int kch = K / kChunkK;
   const int cg = gemm_cta_group(kch);
   const int m_tiles = ((B + kTileM * cg - 1) / (kTileM * cg)) * cg;     // a multiple of cg
   const int rows_padded = m_tiles * kTileM;
-  const int kc = (int)std::min<int64_t>(cand_count(kk), n);
+  const int kc = (int)std::min<int64_t>(kc_want > 0 ? kc_want : cand_count(kk), n);
   GemmPlan plan;
   plan_gemm(kch, m_tiles, cg, &plan);
   const int tn = plan.tn;
@@ -971,15 +974,22 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   VS_CUDA(cudaMemcpyAsync(&h_bad, nbad, 4, cudaMemcpyDeviceToHost, stream));
   VS_CUDA(cudaStreamSynchronize(stream));
   if (h_bad == 0) return VS_OK;
-  s->fallbacks.fetch_add(h_bad);
-  // exact fp32 scan for the queries that could not be certified
+  // second chance / exact fp32 scan for the queries that could not be certified
   float* gq = nullptr; float* ts = nullptr; int32_t* ti = nullptr;
   VS_CUDA(cudaMallocAsync((void**)&gq, (size_t)h_bad * s->dim * 4, stream));
   VS_CUDA(cudaMallocAsync((void**)&ts, (size_t)h_bad * kk * 4, stream));
   VS_CUDA(cudaMallocAsync((void**)&ti, (size_t)h_bad * kk * 4, stream));
   gather_queries_kernel<<<std::min(1184, (h_bad * s->dim + 255) / 256), 256, 0, stream>>>(q, s->dim, bad, h_bad, gq);
   count_launch();
-  int rc = scan_queries_exact(s, n, gq, h_bad, kk, scan_tma, ts, ti, kk, stream);
+  int rc;
+  const int kc_retry = std::min(4 * kc, kMaxCand);
+  if (kc_want == 0 && kc_retry > kc && (int64_t)kc_retry * 8 <= n) {
+    s->retries.fetch_add(h_bad);
+    rc = gemm_block(s, n, gq, h_bad, kk, true, scan_tma, ts, ti, kk, kc_retry, stream);
+  } else {
+    s->fallbacks.fetch_add(h_bad);
+    rc = scan_queries_exact(s, n, gq, h_bad, kk, scan_tma, ts, ti, kk, stream);
+  }
   if (!rc) {
     scatter_results_kernel<<<std::min(1184, (h_bad * kk + 255) / 256), 256, 0, stream>>>(ts, ti, kk, bad, h_bad,
                                                                                        out_scores, out_ids, out_stride);
@@ -1002,7 +1012,7 @@ int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certif
     const int nb = std::min(kMaxQueriesPerLaunch, B - b0);
     if (int rc = gemm_block(s, n, q + (size_t)b0 * s->dim, nb, kk, certify, scan_tma,
                             out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride, out_stride,
-                            stream))
+                            0, stream))
       return rc;
   }
   return VS_OK;

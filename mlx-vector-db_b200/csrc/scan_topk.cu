@@ -495,12 +495,12 @@ static int launch_one(ScanParams p, bool use_tma, int num_sms, int* nlists_out, 
 template <int QB, bool L2, int FMT>
 static int launch_r(const ScanParams& p, int r, bool use_tma, int num_sms, int* nl, bool dry,
                     cudaStream_t st) {
-  switch (r) {
+  switch (r) {   // QB * R <= 32 accumulators per lane
     case 1: return launch_one<QB, 1, L2, FMT>(p, use_tma, num_sms, nl, dry, st);
     case 2: return launch_one<QB, 2, L2, FMT>(p, use_tma, num_sms, nl, dry, st);
-    case 4: if constexpr (QB <= 4) return launch_one<QB, 4, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
-    case 8: if constexpr (QB <= 2) return launch_one<QB, 8, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
-    case 16: if constexpr (QB == 1) return launch_one<QB, 16, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
+    case 4: return launch_one<QB, 4, L2, FMT>(p, use_tma, num_sms, nl, dry, st);
+    case 8: if constexpr (QB <= 4) return launch_one<QB, 8, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
+    case 16: if constexpr (QB <= 2) return launch_one<QB, 16, L2, FMT>(p, use_tma, num_sms, nl, dry, st); break;
   }
   set_error("internal: unsupported rows-per-warp");
   return VS_ERR_INVALID;
@@ -526,10 +526,10 @@ int launch_scan(const ScanParams& base, int qb, bool l2, int fmt, bool use_tma, 
   p.warps = scan_warps_for(qb, p.k);
   const int ew = env_int("B200VS_SCAN_WARPS", 0);
   if (ew > 0 && ew <= kMaxScanWarps && (size_t)ew * qb * p.k * 8 <= 64 * 1024) p.warps = ew;
-  // rows in flight per warp: bounded by the V = QB*R <= 16 accumulators
-  int r = 16 / qb;
+  // rows in flight per warp: V = QB*R accumulators per lane (16 by default, up to 32)
+  int r = qb == 1 ? 16 : 32 / qb;      // measured: 10M x 128 batch 8 runs 1.5x faster at V = 32
   const int er = env_int("B200VS_SCAN_R", 0);
-  if (er > 0 && er * qb <= 16 && (er & (er - 1)) == 0) r = er;
+  if (er > 0 && er * qb <= 32 && er <= 16 && (er & (er - 1)) == 0) r = er;
   const int row_bytes = p.vec_per_row * 16;
   if (use_tma && p.warps > kMaxTmaWarps) p.warps = kMaxTmaWarps;
   if (use_tma) {

@@ -6,7 +6,7 @@
 
 namespace vs {
 
-constexpr int kMaxScanWarps = 16;   // upper bound on consumer warps per CTA (LDG variant)
+constexpr int kMaxScanWarps = 12;   // upper bound on consumer warps per CTA (register budget)
 constexpr int kDefScanWarps = 12;   // default consumer warps (8 when the k-lists are large)
 constexpr int kMaxTmaWarps = 12;    // TMA variant: register budget of a 1-CTA/SM kernel
 constexpr int kMaxQB = 8;           // queries scored per pass over the database

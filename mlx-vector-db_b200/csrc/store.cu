@@ -374,6 +374,7 @@ int vs_destroy(vs_store* s) {
 
 int64_t vs_count(const vs_store* s) { return s ? s->count.load(std::memory_order_acquire) : 0; }
 int64_t vs_fallback_count(const vs_store* s) { return s ? s->fallbacks.load() : 0; }
+int64_t vs_retry_count(const vs_store* s) { return s ? s->retries.load() : 0; }
 
 int64_t vs_memory_bytes(const vs_store* s) {
   if (!s) return 0;

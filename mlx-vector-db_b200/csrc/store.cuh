@@ -41,7 +41,8 @@ struct vs_store {
   int num_sms = 148;
   int64_t max_rows = 0;
   std::atomic<int64_t> count{0};
-  std::atomic<int64_t> fallbacks{0};
+  std::atomic<int64_t> fallbacks{0};   // queries re-run through the exact scan by the GEMM path
+  std::atomic<int64_t> retries{0};     // queries retried with 4x the candidates first
   std::mutex mu;                 // one writer at a time (append / reset)
   cudaEvent_t append_done = nullptr;   // recorded after the last append's kernels
   cudaStream_t append_stream = nullptr;

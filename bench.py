@@ -357,7 +357,7 @@ def run_b200(args):
         _cabi.check(lib.vs_profile_read(kind, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
-    def measure(st, n, d, B, k, steps, warmup, with_e2e=True):
+    def measure(st, n, d, B, k, steps, warmup, with_e2e=True, wl_name=""):
         gq = torch.Generator().manual_seed(QUERY_SEED)
         if args.dist == "uniform":
             q_host = torch.rand((B, d), generator=gq, dtype=torch.float32).pin_memory()
@@ -434,6 +434,15 @@ def run_b200(args):
                                "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
                                "launches": int(scan_n), "avg_launch_ms": per,
                                "kernel_share_of_step": scan_ms / ms}
+        if world == 1 and "roofline" in res:
+            tp = ROOT / "profiles" / "traffic_r01.json"
+            if tp.exists():
+                kind = "gemm" if res["roofline"]["bound"] == "tensor" else "scan"
+                ent = json.loads(tp.read_text()).get(f"{wl_name}|{B}|{kind}")
+                if ent:
+                    res["roofline"]["traffic"] = ent["bytes"]
+                    res["roofline"]["traffic_note"] = ("DRAM bytes per step from the committed ncu capture "
+                                                       "(profiles/traffic_r01.json): " + ent["note"])
         # ---- end to end: host buffers in, host buffers out, every step ----
         if with_e2e:
             out_s = torch.empty((B, k), dtype=torch.float32).pin_memory()
@@ -468,7 +477,7 @@ def run_b200(args):
     n, d = WORKLOADS[args.workload]
     B, k = args.batch, args.k
     st = build_store(n, d, args.mode)
-    main = measure(st, n, d, B, k, args.steps, args.warmup)
+    main = measure(st, n, d, B, k, args.steps, args.warmup, wl_name=args.workload)
 
     # cheap end-of-run sanity (not parity -- tests/ do that): rank-1 score bound, sortedness
     ids_h = main["ids"].cpu().numpy()
@@ -481,7 +490,7 @@ def run_b200(args):
     do_extras = args.extras if args.extras >= 0 else (1 if world == 1 else 0)
     if do_extras:
         short = max(3, min(args.steps, 10))
-        r = measure(st, n, d, 1, k, max(20, args.steps), args.warmup)
+        r = measure(st, n, d, 1, k, max(20, args.steps), args.warmup, wl_name=args.workload)
         extras.append({"workload": f"{args.workload} batch 1", "qps": r["qps"], "ms_per_step": r["ms_per_step"],
                        "roofline": r.get("roofline"), "e2e_qps": r["e2e"]["value"]})
         r = measure(st, n, d, 32, k, max(20, args.steps), args.warmup)
@@ -500,7 +509,7 @@ def run_b200(args):
             n2, d2 = WORKLOADS[name]
             st2 = build_store(n2, d2, args.mode)
             for b2 in batches:
-                r = measure(st2, n2, d2, b2, k, max(20, args.steps) if b2 == 1 else short, args.warmup)
+                r = measure(st2, n2, d2, b2, k, max(20, args.steps) if b2 == 1 else short, args.warmup, wl_name=name)
                 extras.append({"workload": f"{name} batch {b2}", "qps": r["qps"],
                                "ms_per_step": r["ms_per_step"], "roofline": r.get("roofline"),
                                "e2e_qps": r["e2e"]["value"]})

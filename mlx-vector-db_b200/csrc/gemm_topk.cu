@@ -65,7 +65,8 @@ struct GemmParams {
   const float* tau;         // (nq,) filter threshold (kModeFilter)
   float* cand_score;        // (lists, m_tiles*128, kCandCap)
   int32_t* cand_id;
-  int32_t* cand_cnt;        // STREAMING only: (lists, m_tiles*128) running counts, zeroed by the host
+  int32_t* cand_cnt;        // (lists, m_tiles*128) candidates per list, zeroed by the host (STREAMING keeps
+                            // its running counts here, RESIDENT writes them at the end)
   int32_t* overflow;        // (m_tiles*128,) set to 1 when a buffer overflowed
   float* gmax;              // kModeMax: (m_tiles*128, n_tiles)
   float* dump;              // kModeDump: (nq, dump_ld)
@@ -490,14 +491,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
       }
     }
-    // close the candidate lists: unused slots get id -1
+    // publish the candidate counts (K4 reads only the first `count` slots of each list)
     if (MODE == kModeFilter) {
       for (int mt = grp; mt < m_count; mt += 2) {        // this warp group's query tiles
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
-        const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];
         if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }
-        for (int e = c; e < kCandCap; ++e) p.cand_id[cbase + e] = -1;
+        p.cand_cnt[(int64_t)list * q_total + q] = c;
       }
     }
   }
@@ -928,7 +928,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   GemmParams p = {};
   p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = fp16 ? 1 : 0;
   p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
-  if (plan.mt == 0) VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
+  VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
   if (sampled) {
     // pass 1: per-query maxima of the sample tiles -> tau = kc-th largest (a lower bound of
     // the kc-th best score overall)
@@ -954,6 +954,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
     MergeParams m = {};
     m.ck = cs; m.ci = ci; m.per_query = (int64_t)lists * kCandCap; m.chunk = kCandCap;
     m.chunk_stride = (int64_t)rows_padded * kCandCap; m.query_stride = kCandCap; m.list_len = 0;
+    m.counts = ccnt; m.count_stride = rows_padded;
     m.k = kc; m.tau = nullptr; m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
     if (int rc = launch_merge(m, B, stream)) return rc;
   }

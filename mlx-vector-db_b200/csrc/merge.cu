@@ -20,6 +20,10 @@ __device__ __forceinline__ int64_t cand_addr(const MergeParams& p, int b, int64_
 }
 __device__ __forceinline__ bool cand_load(const MergeParams& p, int b, int64_t i, float thr,
                                           float& key, int& id) {
+  if (p.counts) {
+    const int64_t c = i / p.chunk;
+    if (i - c * p.chunk >= p.counts[c * p.count_stride + b]) return false;
+  }
   const int64_t a = cand_addr(p, b, i);
   id = p.ci ? p.ci[a] : (int)i;     // no id array: the id is the candidate's position
   if (id < 0) return false;

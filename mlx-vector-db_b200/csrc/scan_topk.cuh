@@ -70,6 +70,8 @@ struct MergeParams {
   int32_t* out_i;
   int64_t out_stride;
   float* kth_out;          // nullable: (B,) the k-th best key (-inf when fewer than k candidates)
+  const int32_t* counts;   // nullable: chunk c of query b holds counts[c * count_stride + b] valid
+  int64_t count_stride;    //           candidates (its remaining slots are not read)
 };
 int launch_merge(const MergeParams& p, int B, cudaStream_t stream);
 // scan-list layout: candidates of query b contiguous at b * per_query

@@ -235,6 +235,35 @@ def config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args):
     return out
 
 
+def k1_append_throughput(dev, lib, _cabi, ShardedVectorStore, args):
+    """K1 append_norm alone: device-resident rows appended into a fresh store; bytes = rows read
+    + fp32 master written + 16-bit shadow written + norms (HBM-bound copy-like kernel)."""
+    import torch
+    out = {"workload": "K1 append_norm (device-resident rows -> arena, norms, 16-bit shadow)"}
+    for n, d in ((4_000_000, 128), (500_000, 1536)):
+        st = ShardedVectorStore(d, "cosine", device=dev, shadow_bf16=True, max_vectors_per_shard=n + 16,
+                                search_mode=args.mode)
+        rows = torch.randn((n, d), device=dev, dtype=torch.float32)
+        st.add_vectors(rows)                       # maps the arena chunks (host-side VMM calls)
+        torch.cuda.synchronize()
+        _cabi.check(lib.vs_reset(st.shard.handle))  # forget the rows, keep the mapped arena
+        st.total = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st.add_vectors(rows)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        ld16 = (d + 63) // 64 * 64
+        nbytes = n * (d * 4 + d * 4 + ld16 * 2 + 12)
+        out[f"{n}x{d}"] = {"ms": ms, "rows_per_s": n / (ms * 1e-3), "GBps": nbytes / (ms * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / 6466.5}
+        st.close()
+        del rows
+        torch.cuda.empty_cache()
+    return out
+
+
 def config_e_streaming(dev, lib, _cabi, ShardedVectorStore, args):
     """BASELINE config E: 5M x 384 mixed streaming workload -- the store starts at 1M rows and
     grows to 5M by 10 000-row appends (K1, in-place arena growth), each followed by a batch-256
@@ -518,6 +547,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
         extras.append(config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args))
         extras.append(config_e_streaming(dev, lib, _cabi, ShardedVectorStore, args))
+        extras.append(k1_append_throughput(dev, lib, _cabi, ShardedVectorStore, args))
     else:
         st.close()
 

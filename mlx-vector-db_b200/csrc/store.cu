@@ -197,7 +197,23 @@ void Arena::destroy() {
 
 // --------------------------------------------------------- K1 append_norm
 // One warp per appended row: copy into the master arena (padded stride), row norm with the
-// 1e-8 clamp of service/optimized_vector_store.py:36-38, ||x||^2, optional bf16 shadow row.
+// 1e-8 clamp of service/optimized_vector_store.py:36-38, ||x||^2, optional 16-bit shadow row
+// (fp16 of x/||x|| for cosine, bf16 of x otherwise) and the two maxima the GEMM path's
+// certification needs: max ||v - v^|| and max ||v^|| over all shadow rows (kept per warp, one
+// atomicMax per warp at the end).  VEC: 128-bit accesses when dim % 4 == 0.
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool fp16, float& ra, float& rb) {
+  if (fp16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    ra = f.x; rb = f.y;
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  ra = __bfloat162float(h.x); rb = __bfloat162float(h.y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
                    int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
@@ -207,15 +223,29 @@ append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restr
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float e_max = 0.f, s_max = 0.f;
   for (int64_t r = warp; r < m; r += nwarps) {
     const float* s = src + r * src_ld;
     float* d = rows + (n0 + r) * (int64_t)ld;
     const bool in_place = (s == d);
     float acc = 0.f;
-    for (int c = lane; c < ld; c += 32) {
-      float v = c < dim ? s[c] : 0.f;
-      acc = fmaf(v, v, acc);
-      if (!in_place) d[c] = v;
+    if (VEC) {
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* d4 = reinterpret_cast<float4*>(d);
+      const int nvec = dim >> 2;
+      // same per-lane order as the scalar path is not required: norms are defined by this kernel
+      for (int c = lane; c < nvec; c += 32) {
+        const float4 v = s4[c];
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+        acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+        if (!in_place) d4[c] = v;
+      }
+    } else {
+      for (int c = lane; c < ld; c += 32) {
+        float v = c < dim ? s[c] : 0.f;
+        acc = fmaf(v, v, acc);
+        if (!in_place) d[c] = v;
+      }
     }
     const float tot = warp_sum(acc);
     const float nrm = fmaxf(sqrtf(tot), 1e-8f);
@@ -225,36 +255,55 @@ append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restr
       if (gids != nullptr) gids[n0 + r] = (int32_t)(gid0 + r);
     }
     if (shadow != nullptr) {
-      // bf16 shadow row + what the GEMM path's certification needs: the largest rounding
-      // error norm ||v - bf16(v)|| and the largest shadow norm ||bf16(v)|| over all rows
-      __nv_bfloat16* sh = shadow + (n0 + r) * (int64_t)ld16;
+      // cosine: unit-norm rows fit fp16's range and keep 11 significant bits (8x smaller
+      // rounding error than bf16 -> far tighter certification); raw rows keep bf16's range
+      const bool fp16 = normalize_shadow != 0;
       float e2 = 0.f, s2 = 0.f;
-      for (int c = lane; c < ld16; c += 32) {
-        float v = c < dim ? s[c] : 0.f;
-        if (normalize_shadow) v = v / nrm;
-        // cosine: unit-norm rows fit fp16's range and keep 11 significant bits (8x smaller
-        // rounding error than bf16 -> far tighter certification); raw rows keep bf16's range
-        float vb;
-        if (normalize_shadow) {
-          const __half h = __float2half_rn(v);
-          reinterpret_cast<__half*>(sh)[c] = h;
-          vb = __half2float(h);
-        } else {
-          const __nv_bfloat16 h = __float2bfloat16_rn(v);
-          sh[c] = h;
-          vb = __bfloat162float(h);
+      if (VEC) {
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        uint2* sh2 = reinterpret_cast<uint2*>(shadow + (n0 + r) * (int64_t)ld16);
+        const int nvec = dim >> 2;
+        for (int c = lane; c < (ld16 >> 2); c += 32) {
+          float4 v = c < nvec ? s4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fp16) { v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm; }
+          float r0, r1, r2, r3;
+          uint2 o;
+          o.x = pack16(v.x, v.y, fp16, r0, r1);
+          o.y = pack16(v.z, v.w, fp16, r2, r3);
+          sh2[c] = o;
+          float t;
+          t = v.x - r0; e2 = fmaf(t, t, e2); s2 = fmaf(r0, r0, s2);
+          t = v.y - r1; e2 = fmaf(t, t, e2); s2 = fmaf(r1, r1, s2);
+          t = v.z - r2; e2 = fmaf(t, t, e2); s2 = fmaf(r2, r2, s2);
+          t = v.w - r3; e2 = fmaf(t, t, e2); s2 = fmaf(r3, r3, s2);
         }
-        const float dlt = v - vb;
-        e2 = fmaf(dlt, dlt, e2);
-        s2 = fmaf(vb, vb, s2);
+      } else {
+        __nv_bfloat16* sh = shadow + (n0 + r) * (int64_t)ld16;
+        for (int c = lane; c < ld16; c += 32) {
+          float v = c < dim ? s[c] : 0.f;
+          if (fp16) v = v / nrm;
+          float vb;
+          if (fp16) {
+            const __half h = __float2half_rn(v);
+            reinterpret_cast<__half*>(sh)[c] = h;
+            vb = __half2float(h);
+          } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            sh[c] = h;
+            vb = __bfloat162float(h);
+          }
+          const float dlt = v - vb;
+          e2 = fmaf(dlt, dlt, e2);
+          s2 = fmaf(vb, vb, s2);
+        }
       }
-      e2 = warp_sum(e2);
-      s2 = warp_sum(s2);
-      if (lane == 0) {   // non-negative floats order like their bit patterns
-        atomicMax(bounds + 0, __float_as_uint(sqrtf(e2) * 1.00001f));
-        atomicMax(bounds + 1, __float_as_uint(sqrtf(s2) * 1.00001f));
-      }
+      e_max = fmaxf(e_max, sqrtf(warp_sum(e2)));
+      s_max = fmaxf(s_max, sqrtf(warp_sum(s2)));
     }
+  }
+  if (shadow != nullptr && lane == 0) {   // non-negative floats order like their bit patterns
+    atomicMax(bounds + 0, __float_as_uint(e_max * 1.00001f));
+    atomicMax(bounds + 1, __float_as_uint(s_max * 1.00001f));
   }
 }
 
@@ -453,9 +502,11 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
     }
     const int warps_per_block = 8;
     int64_t blocks = (mm + warps_per_block - 1) / warps_per_block;
-    const int64_t cap = (int64_t)s->num_sms * 8;
+    const int64_t cap = (int64_t)s->num_sms * 8;      // 8 CTAs of 8 warps per SM: a grid multiple of 148
     if (blocks > cap) blocks = cap;
-    append_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+    const bool vec = (s->dim & 3) == 0 && (ksrc_ld & 3) == 0 && ((uintptr_t)ksrc & 15) == 0;
+    auto kern = vec ? append_norm_kernel<true> : append_norm_kernel<false>;
+    kern<<<(unsigned)blocks, 256, 0, stream>>>(
         ksrc, ksrc_ld, master, s->ld, s->dim, n0 + off, mm, (float*)s->norms.ptr(),
         (float*)s->sqnorms.ptr(), s->shadow ? (__nv_bfloat16*)s->shadow_rows.ptr() : nullptr,
         s->ld16, s->metric == VS_METRIC_COSINE ? 1 : 0,

@@ -213,6 +213,69 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool fp16, float& r
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Fast path for rows of at most 128 floats (one float4 per lane): R rows per warp iteration are
+// loaded together (latency hiding) and stay in registers for the norm, the copy and the shadow.
+constexpr int kAppendR = 4;
+__global__ void __launch_bounds__(256)
+append_norm_small_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
+                         int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
+                         float* __restrict__ sqnorms, __nv_bfloat16* __restrict__ shadow, int ld16,
+                         int normalize_shadow, int32_t* __restrict__ gids, int64_t gid0,
+                         uint32_t* __restrict__ bounds) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nvec = dim >> 2;                 // <= 32
+  const bool have = lane < nvec;
+  const bool fp16 = normalize_shadow != 0;
+  float e_max = 0.f, s_max = 0.f;
+  for (int64_t r0 = warp * kAppendR; r0 < m; r0 += nwarps * kAppendR) {
+    float4 v[kAppendR];
+#pragma unroll
+    for (int j = 0; j < kAppendR; ++j) {
+      const int64_t r = r0 + j < m ? r0 + j : r0;
+      v[j] = have ? reinterpret_cast<const float4*>(src + r * src_ld)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kAppendR; ++j) {
+      if (r0 + j >= m) break;                // warp-uniform
+      const int64_t r = r0 + j;
+      float acc = 0.f;
+      acc = fmaf(v[j].x, v[j].x, acc); acc = fmaf(v[j].y, v[j].y, acc);
+      acc = fmaf(v[j].z, v[j].z, acc); acc = fmaf(v[j].w, v[j].w, acc);
+      const float tot = warp_sum(acc);
+      const float nrm = fmaxf(sqrtf(tot), 1e-8f);
+      float* d = rows + (n0 + r) * (int64_t)ld;
+      if (have && d != src + r * src_ld) reinterpret_cast<float4*>(d)[lane] = v[j];
+      if (lane == 0) {
+        norms[n0 + r] = nrm;
+        sqnorms[n0 + r] = tot;
+        if (gids != nullptr) gids[n0 + r] = (int32_t)(gid0 + r);
+      }
+      if (shadow != nullptr) {
+        float4 w = v[j];
+        if (fp16) { w.x = w.x / nrm; w.y = w.y / nrm; w.z = w.z / nrm; w.w = w.w / nrm; }
+        float q0, q1, q2, q3;
+        uint2 o;
+        o.x = pack16(w.x, w.y, fp16, q0, q1);
+        o.y = pack16(w.z, w.w, fp16, q2, q3);
+        if (lane < (ld16 >> 2)) reinterpret_cast<uint2*>(shadow + (n0 + r) * (int64_t)ld16)[lane] = o;
+        float e2 = 0.f, s2 = 0.f, t;
+        t = w.x - q0; e2 = fmaf(t, t, e2); s2 = fmaf(q0, q0, s2);
+        t = w.y - q1; e2 = fmaf(t, t, e2); s2 = fmaf(q1, q1, s2);
+        t = w.z - q2; e2 = fmaf(t, t, e2); s2 = fmaf(q2, q2, s2);
+        t = w.w - q3; e2 = fmaf(t, t, e2); s2 = fmaf(q3, q3, s2);
+        e_max = fmaxf(e_max, sqrtf(warp_sum(e2)));
+        s_max = fmaxf(s_max, sqrtf(warp_sum(s2)));
+      }
+    }
+  }
+  if (shadow != nullptr && lane == 0) {
+    atomicMax(bounds + 0, __float_as_uint(e_max * 1.00001f));
+    atomicMax(bounds + 1, __float_as_uint(s_max * 1.00001f));
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
@@ -506,6 +569,12 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
     if (blocks > cap) blocks = cap;
     const bool vec = (s->dim & 3) == 0 && (ksrc_ld & 3) == 0 && ((uintptr_t)ksrc & 15) == 0;
     auto kern = vec ? append_norm_kernel<true> : append_norm_kernel<false>;
+    // rows of <= 128 floats whose 16-bit shadow row is at most 128 elements wide (ld16/4 <= 32 lanes)
+    if (vec && s->dim <= 128 && s->ld == s->dim && s->ld16 <= 128) {
+      kern = append_norm_small_kernel;
+      blocks = (mm + warps_per_block * kAppendR - 1) / (warps_per_block * kAppendR);
+      if (blocks > cap) blocks = cap;
+    }
     kern<<<(unsigned)blocks, 256, 0, stream>>>(
         ksrc, ksrc_ld, master, s->ld, s->dim, n0 + off, mm, (float*)s->norms.ptr(),
         (float*)s->sqnorms.ptr(), s->shadow ? (__nv_bfloat16*)s->shadow_rows.ptr() : nullptr,

@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--extras", type=int, default=-1,
                     help="also measure the other BASELINE shapes/batches (default: on at N=1)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--clocks", default="smi", choices=["smi", "nvml", "off"],
+                    help="how SM clocks / throttle reasons are sampled during the timed region")
     ap.add_argument("--verify", type=int, default=1)
     return ap.parse_args()
 
@@ -110,6 +112,72 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None,
                 "power_w_max": max(power) if power else None, "samples": len(sm),
                 "reasons": sorted(reasons)}
+
+
+class NvmlSampler:
+    """Same record through NVML from a background thread of this process (no nvidia-smi process
+    polling the driver): SM clock, power and throttle reasons every 50 ms."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples, self.power, self.bits = [], [], 0
+        self.smax = None
+        self.stop_flag = False
+        self.thread = None
+
+    def start(self):
+        import threading
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.thread = None
+            return
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    try:
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.05)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        time.sleep(0.06)
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(sm),
+                "reasons": sorted(v for b, v in self.REASONS.items() if self.bits & b), "source": "nvml"}
+
+
+class NoSampler:
+    def __init__(self, gpu_index): pass
+    def start(self): pass
+    def stop(self): return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling disabled"]}
+
+
+def make_sampler(kind: str, gpu_index: int):
+    return {"smi": ClockSampler, "nvml": NvmlSampler, "off": NoSampler}[kind](gpu_index)
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -403,7 +471,7 @@ def run_b200(args):
         barrier()
         launches0 = lib.vs_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local_rank)
+        sampler = make_sampler(args.clocks, local_rank)
         if rank == 0:
             sampler.start()
         e0.record()
@@ -419,7 +487,7 @@ def run_b200(args):
             # the timed region was too short for nvidia-smi's 100 ms sampling: keep the same step
             # running (untimed, every rank -- the all-gather is collective) and sample under load
             extra = int(min(20000, 700.0 / max(ms / steps, 1e-3))) + 1
-            sampler = ClockSampler(local_rank)
+            sampler = make_sampler(args.clocks, local_rank)
             if rank == 0:
                 sampler.start()
                 time.sleep(0.05)

@@ -116,6 +116,7 @@ class ShardedVectorStore:
         factory = shard_factory or NativeShard
         self.shard = factory(dimension, metric, device, shadow_bf16, max_vectors_per_shard, search_mode)
         self.total = 0
+        self._bufs = {}
 
     # ------------------------------------------------------------------ add
     def add_vectors(self, vectors) -> dict:
@@ -151,11 +152,22 @@ class ShardedVectorStore:
         if B == 0 or kk == 0:
             return (torch.zeros((B, 0), dtype=torch.int32, device=q.device),
                     torch.zeros((B, 0), dtype=torch.float32, device=q.device))
-        pack = self.shard.new_pack(B, kk)
+        # The buffers the collective touches are kept per (B, k) instead of being re-allocated:
+        # tensors used on NCCL's stream go back to torch's caching allocator only after that
+        # stream has passed them, so a host that runs ahead of the GPU would otherwise fall
+        # through to cudaMalloc (a device-wide synchronisation) every few steps.
+        key = (B, kk)
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            pack = self.shard.new_pack(B, kk)
+            flat = torch.empty((self.world * pack.numel(),), dtype=pack.dtype, device=pack.device)
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            bufs = self._bufs[key] = (pack, flat)
+        pack, flat = bufs
         self.shard.search_into(q, kk, pack)
         if self.world == 1:
-            return pack[1], pack[0].view(torch.float32)
-        flat = torch.empty((self.world * pack.numel(),), dtype=pack.dtype, device=pack.device)
+            return pack[1].clone(), pack[0].view(torch.float32).clone()
         dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
         return self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
 

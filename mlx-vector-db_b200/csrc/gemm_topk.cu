@@ -841,7 +841,7 @@ bool gemm_supported(const vs_store* s, int64_t n, int B, int kk) {
   if (!gemm_enabled() || !s->shadow) return false;
   if (s->metric == VS_METRIC_EUCLIDEAN) return false;       // L2 candidates: bf16 scan path
   if (B < gemm_min_batch() || s->dim > 8192) return false;
-  if (cand_count(kk) > 64) return false;
+  if (cand_count(kk) > kMaxCand) return false;            // k <= 128
   if (n < 65536) return false;                              // small stores: the scan is enough
   return true;
 }
@@ -1008,7 +1008,7 @@ int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certif
               float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
   if (!s->shadow) { set_error("store was created without a bf16 shadow copy"); return VS_ERR_STATE; }
   if (s->metric == VS_METRIC_EUCLIDEAN) { set_error("the GEMM path serves cosine and dot_product"); return VS_ERR_STATE; }
-  if (cand_count(kk) > 64) { set_error("invalid argument: k too large for the GEMM path (k <= 32)"); return VS_ERR_INVALID; }
+  if (cand_count(kk) > kMaxCand) { set_error("invalid argument: k too large for the GEMM path (k <= 128)"); return VS_ERR_INVALID; }
   for (int b0 = 0; b0 < B; b0 += kMaxQueriesPerLaunch) {
     const int nb = std::min(kMaxQueriesPerLaunch, B - b0);
     if (int rc = gemm_block(s, n, q + (size_t)b0 * s->dim, nb, kk, certify, scan_tma,

@@ -89,7 +89,9 @@ SEARCH_SHAPES = [
     (70001, 256, 200, 10),
     (66000, 384, 128, 10),     # streaming kernel
     (66000, 768, 64, 1),
-    (90000, 128, 100, 32),     # largest k the path takes (kc = 64)
+    (90000, 128, 100, 32),
+    (80000, 256, 40, 100),     # top-100: kc = 200 candidates per query
+    (70000, 128, 16, 128),     # largest k the path takes (kc = 256)
 ]
 
 

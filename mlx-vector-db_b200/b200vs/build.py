@@ -22,6 +22,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
 ]
+# tuning knob (diagnostic): B200VS_EPI_GROUPS=4 builds K3 with 16 epilogue warps
+if os.environ.get("B200VS_EPI_GROUPS"):
+    NVCC_FLAGS.append("-DVS_EPI_GROUPS=" + os.environ["B200VS_EPI_GROUPS"])
 
 
 def _nvcc() -> str:

@@ -41,7 +41,11 @@
 
 namespace vs {
 
-constexpr int kGemmThreads = 384;       // 4 control warps + 8 epilogue warps
+#ifndef VS_EPI_GROUPS
+#define VS_EPI_GROUPS 2
+#endif
+constexpr int kEpiGroups = VS_EPI_GROUPS;                 // epilogue warp groups (4 warps each)
+constexpr int kGemmThreads = 128 + 128 * kEpiGroups;      // 4 control warps + the epilogue warps
 constexpr int kTileM = 128;              // queries per m-tile = TMEM lanes
 constexpr int kChunkK = 64;              // bf16 elements per 128-byte swizzled row
 constexpr int kChunkBytes = 128 * 128;   // 128 rows x 128 B
@@ -381,7 +385,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // warp take the rare path, which re-reads the offending 8-column groups from TMEM (short
     // code: the hot loop must stay resident in the instruction cache).
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
-    const int grp = (warp - 4) >> 2;                    // warps 4-7 take even m-tiles, 8-11 odd ones
+    const int grp = (warp - 4) >> 2;                    // query tile mt belongs to group mt % kEpiGroups
     const int row = quad * 32 + lane;                   // query row inside the m-tile
     const int list = RES ? uig : unit;                  // candidate list of this unit
     const int64_t q_total = (int64_t)p.m_tiles * kTileM;
@@ -400,7 +404,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int nt = uig + i * units_in_group;
 #pragma unroll 1
       for (int mt = 0; mt < m_count; ++mt, ++it) {
-        if ((mt & 1) != grp) continue;
+        if ((mt % kEpiGroups) != grp) continue;
         const int slot = it % SLOTS;
         const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
@@ -493,7 +497,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     // publish the candidate counts (K4 reads only the first `count` slots of each list)
     if (MODE == kModeFilter) {
-      for (int mt = grp; mt < m_count; mt += 2) {        // this warp group's query tiles
+      for (int mt = grp; mt < m_count; mt += kEpiGroups) {   // this warp group's query tiles
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
         int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];
         if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }

@@ -51,6 +51,8 @@ constexpr int kChunkK = 64;              // bf16 elements per 128-byte swizzled 
 constexpr int kChunkBytes = 128 * 128;   // 128 rows x 128 B
 constexpr int kTmemCols = 512;
 constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
+constexpr int kMaxGroupTiles = 4;        // pass 1: tiles (of one CTA) per maximum
+constexpr int kGlobalCap = 4096;         // candidate slots per query over all CTAs (= K4's capacity)
 constexpr int kMaxQueriesPerLaunch = 2048;
 
 enum { kModeFilter = 0, kModeMax = 1, kModeDump = 2 };
@@ -72,7 +74,13 @@ struct GemmParams {
   int32_t* cand_cnt;        // (lists, m_tiles*128) candidates per list, zeroed by the host (STREAMING keeps
                             // its running counts here, RESIDENT writes them at the end)
   int32_t* overflow;        // (m_tiles*128,) set to 1 when a buffer overflowed
-  float* gmax;              // kModeMax: (m_tiles*128, n_tiles)
+  float* glist_s;           // (m_tiles*128, kGlobalCap) dense per-query candidate lists: at the end of the
+  int32_t* glist_i;         //   kernel every thread moves its private candidates here (one atomicAdd on
+  int32_t* gcount;          //   gcount[q] per (CTA, query)), so K4 reads contiguous entries only
+  float* gmax;              // kModeMax: (m_tiles*128, n_groups) maxima of groups of kMaxGroupTiles tiles
+  int n_groups;             //   = units_in_group * groups_per_unit
+  int groups_per_unit;
+  int group_tiles;          //   tiles (of one unit) per maximum: kMaxGroupTiles, or 1 when tiles are scarce
   float* dump;              // kModeDump: (nq, dump_ld)
   int64_t dump_ld;
 };
@@ -392,6 +400,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     constexpr int NST = RES ? MT : 1;
     float tau_l[NST];                                   // RESIDENT: per-thread state of its
     int cnt_l[NST];                                     // query tiles (dynamically indexed)
+    float rmax_l[MODE == kModeMax ? 16 : 1];            // pass 1: running maximum per query tile
+    if (MODE == kModeMax)
+      for (int mt = 0; mt < 16; ++mt) rmax_l[mt] = VS_NEG_INF;
     if (RES && MODE == kModeFilter) {
       for (int mt = 0; mt < NST; ++mt) {
         cnt_l[mt] = 0;
@@ -421,7 +432,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         bar_wait(bar_accf + 8 * slot, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
-        float rmax = VS_NEG_INF;
+        float rmax = MODE == kModeMax ? rmax_l[mt & 15] : VS_NEG_INF;
         float va[32], vb[32];
         tc_ld32(taddr, va);
 #pragma unroll 1
@@ -488,20 +499,41 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           if (CG == 2 && crank != 0) bar_arrive_remote(bar_acce + 8 * slot, 0);
           else bar_arrive(bar_acce + 8 * slot);
         }
-        if (MODE == kModeMax) p.gmax[(int64_t)q * p.n_tiles + nt] = rmax;
+        if (MODE == kModeMax) {
+          // one maximum per kMaxGroupTiles consecutive tiles of this unit
+          if ((i % p.group_tiles) == p.group_tiles - 1 || i == my_tiles - 1) {
+            p.gmax[(int64_t)q * p.n_groups + uig * p.groups_per_unit + i / p.group_tiles] = rmax;
+            rmax = VS_NEG_INF;
+          }
+          rmax_l[mt & 15] = rmax;
+        }
         if (MODE == kModeFilter) {
           if (RES) cnt_l[mt] = c;
           else p.cand_cnt[(int64_t)list * q_total + q] = c;
         }
       }
     }
-    // publish the candidate counts (K4 reads only the first `count` slots of each list)
+    if (MODE == kModeMax) {   // groups this unit has no tiles for
+      for (int g = (my_tiles + p.group_tiles - 1) / p.group_tiles; g < p.groups_per_unit; ++g)
+        for (int mt = grp; mt < m_count; mt += kEpiGroups)
+          p.gmax[(int64_t)(((m_first + mt) * CG + crank) * kTileM + row) * p.n_groups + uig * p.groups_per_unit + g] =
+              VS_NEG_INF;
+    }
+    // move this thread's private candidates into the dense per-query lists
     if (MODE == kModeFilter) {
       for (int mt = grp; mt < m_count; mt += kEpiGroups) {   // this warp group's query tiles
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
+        if (q >= p.nq) continue;
+        const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];
-        if (c > kCandCap) { if (q < p.nq) p.overflow[q] = 1; c = kCandCap; }
-        p.cand_cnt[(int64_t)list * q_total + q] = c;
+        if (c > kCandCap) { p.overflow[q] = 1; c = kCandCap; }
+        if (c == 0) continue;
+        const int base = atomicAdd(p.gcount + q, c);
+        if (base + c > kGlobalCap) { p.overflow[q] = 1; continue; }
+        for (int e = 0; e < c; ++e) {
+          p.glist_s[(int64_t)q * kGlobalCap + base + e] = p.cand_score[cbase + e];
+          p.glist_i[(int64_t)q * kGlobalCap + base + e] = p.cand_id[cbase + e];
+        }
       }
     }
   }
@@ -796,22 +828,36 @@ static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const Gem
   }
 }
 
+// units (CTAs or CTA pairs) a launch uses, its query groups and candidate lists per query
+static void gemm_units(const GemmPlan& plan, int m_tiles, int n_tiles, int num_sms, int* units_out, int* ngroups_out,
+                       int* lists_out) {
+  int units = num_sms / plan.cg;
+  int ngroups = 1, lists;
+  if (plan.mt > 0) {
+    const int um_tiles = m_tiles / plan.cg;
+    ngroups = (um_tiles + plan.mt - 1) / plan.mt;
+    const int64_t want = (int64_t)n_tiles * ngroups;
+    if (want < units) units = (int)want;
+    if (units < ngroups) units = ngroups;
+    lists = (units + ngroups - 1) / ngroups;
+  } else {
+    if (n_tiles < units) units = n_tiles;
+    lists = units;
+  }
+  *units_out = units; *ngroups_out = ngroups; *lists_out = lists;
+}
+
 static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,
                        int num_sms, int* lists_out, cudaStream_t stream) {
   p.stages = plan.stages;
   p.idesc = instr_desc(kTileM * plan.cg, plan.tn, p.fp16 ? 0 : 1);
-  int units = num_sms / plan.cg;                       // CTAs (cg = 1) or CTA pairs (cg = 2)
-  if (plan.mt > 0) {
-    const int um_tiles = p.m_tiles / plan.cg;
-    p.ngroups = (um_tiles + plan.mt - 1) / plan.mt;
-    const int64_t want = (int64_t)p.n_tiles * p.ngroups;
-    if (want < units) units = (int)want;
-    if (units < p.ngroups) units = p.ngroups;
-    if (lists_out) *lists_out = (units + p.ngroups - 1) / p.ngroups;
-  } else {
-    p.ngroups = 1;
-    if (p.n_tiles < units) units = p.n_tiles;
-    if (lists_out) *lists_out = units;
+  int units, lists;
+  gemm_units(plan, p.m_tiles, p.n_tiles, num_sms, &units, &p.ngroups, &lists);
+  if (lists_out) *lists_out = lists;
+  if (p.mode == kModeMax) {
+    const int per_unit = (p.n_tiles + lists - 1) / lists;            // most tiles any unit gets
+    p.groups_per_unit = (per_unit + p.group_tiles - 1) / p.group_tiles;
+    p.n_groups = lists * p.groups_per_unit;
   }
   const int grid = units * plan.cg;
   switch (plan.mt) {
@@ -894,28 +940,39 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   double f = std::sqrt(1920.0 * kc / (double)n);
   if (f > 0.5) f = 0.5;
   if (f < 1.0 / 32) f = 1.0 / 32;
-  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, 4 * kc), 4096);
+  // Maxima are taken over groups of kMaxGroupTiles tiles; at most 4096 groups (merge kernel
+  // capacity), at least 4 kc groups so that the kc best rows rarely share a group.
+  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, 4 * kc * kMaxGroupTiles),
+                                       4096 * kMaxGroupTiles);
   if (s_tiles > (int)(n / tn)) s_tiles = (int)(n / tn);
-  const bool sampled = s_tiles >= 2 * kc;
+  int s_units, s_ngroups, s_lists;
+  gemm_units(plan, m_tiles, s_tiles, s->num_sms, &s_units, &s_ngroups, &s_lists);
+  const int gt = s_tiles / kMaxGroupTiles >= 4 * kc ? kMaxGroupTiles : 1;
+  const int s_groups = s_lists * (((s_tiles + s_lists - 1) / s_lists + gt - 1) / gt);
+  const bool sampled = s_tiles / gt >= 2 * kc && s_groups <= 4096;
 
   const int max_lists = s->num_sms;
   Ws ws;
-  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *c1s, *rk; int32_t *ci, *ccnt, *c1i, *ovf, *bad; int* nbad;
+  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *c1s, *rk, *gls; int32_t *ci, *ccnt, *c1i, *ovf, *bad, *gli, *gcnt; int* nbad;
   ws.want(&qb, (size_t)rows_padded * K);
   ws.want(&qerr, (size_t)rows_padded);
   ws.want(&qlen, (size_t)rows_padded);
   ws.want(&tau, (size_t)rows_padded);
-  ws.want(&gmax, sampled ? (size_t)rows_padded * s_tiles : 1);
+  ws.want(&gmax, sampled ? (size_t)rows_padded * s_groups : 1);
   ws.want(&cs, (size_t)max_lists * rows_padded * kCandCap);
   ws.want(&ci, (size_t)max_lists * rows_padded * kCandCap);
   ws.want(&ccnt, (size_t)max_lists * rows_padded);
+  ws.want(&gls, (size_t)rows_padded * kGlobalCap);
+  ws.want(&gli, (size_t)rows_padded * kGlobalCap);
   ws.want(&c1s, (size_t)B * kc);
   ws.want(&c1i, (size_t)B * kc);
   ws.want(&rk, (size_t)B * kc);
-  ws.want(&ovf, (size_t)rows_padded);
+  int32_t* zeroed;                       // [overflow | gcount | n_bad], cleared by ONE memset
+  ws.want(&zeroed, (size_t)2 * rows_padded + 1);
   ws.want(&bad, (size_t)B);
-  ws.want(&nbad, 1);
   if (int rc = ws.alloc(stream)) return rc;
+  ovf = zeroed; gcnt = zeroed + rows_padded; nbad = zeroed + 2 * rows_padded;
+  VS_CUDA(cudaMemsetAsync(zeroed, 0, ((size_t)2 * rows_padded + 1) * 4, stream));
 
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
@@ -926,21 +983,22 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
                                                                     qerr, qlen);
   count_launch();
   VS_CHECK_LAUNCH();
-  VS_CUDA(cudaMemsetAsync(ovf, 0, (size_t)rows_padded * 4, stream));
-  VS_CUDA(cudaMemsetAsync(nbad, 0, 4, stream));
 
   GemmParams p = {};
   p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = fp16 ? 1 : 0;
   p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
-  VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
+  p.glist_s = gls; p.glist_i = gli; p.gcount = gcnt;
+
+  if (plan.mt == 0)   // STREAMING keeps its running candidate counts in global memory
+    VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
   if (sampled) {
     // pass 1: per-query maxima of the sample tiles -> tau = kc-th largest (a lower bound of
     // the kc-th best score overall)
-    p.mode = kModeMax; p.n_tiles = s_tiles; p.gmax = gmax;
+    p.mode = kModeMax; p.n_tiles = s_tiles; p.gmax = gmax; p.group_tiles = gt;
     if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
     MergeParams m = {};
-    m.ck = gmax; m.ci = nullptr; m.per_query = s_tiles; m.chunk = s_tiles; m.chunk_stride = 0;
-    m.query_stride = s_tiles; m.list_len = 0; m.k = kc; m.tau = nullptr;
+    m.ck = gmax; m.ci = nullptr; m.per_query = s_groups; m.chunk = s_groups; m.chunk_stride = 0;
+    m.query_stride = s_groups; m.list_len = 0; m.k = kc; m.tau = nullptr;
     m.out_s = c1s; m.out_i = c1i; m.out_stride = kc; m.kth_out = tau;      // tau[b] = kc-th largest
     if (int rc = launch_merge(m, B, stream)) return rc;
   } else {
@@ -956,9 +1014,9 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   // K4: best kc candidates by bf16 score
   {
     MergeParams m = {};
-    m.ck = cs; m.ci = ci; m.per_query = (int64_t)lists * kCandCap; m.chunk = kCandCap;
-    m.chunk_stride = (int64_t)rows_padded * kCandCap; m.query_stride = kCandCap; m.list_len = 0;
-    m.counts = ccnt; m.count_stride = rows_padded;
+    m.ck = gls; m.ci = gli; m.per_query = kGlobalCap; m.chunk = kGlobalCap;
+    m.chunk_stride = 0; m.query_stride = kGlobalCap; m.list_len = 0;
+    m.counts = gcnt; m.count_stride = 0;           // query b holds gcnt[b] dense candidates
     m.k = kc; m.tau = nullptr; m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
     if (int rc = launch_merge(m, B, stream)) return rc;
   }

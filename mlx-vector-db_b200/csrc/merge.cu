@@ -117,10 +117,15 @@ merge_topk_kernel(const MergeParams p) {
   }
   __syncthreads();
   // compaction with one shared-memory atomic per warp (ballot + prefix popcount)
-  for (int64_t i0 = 0; i0 < p.per_query; i0 += kMergeThreads) {
+  int64_t limit = p.per_query;
+  if (p.counts && p.chunk >= p.per_query) {          // one dense list: read the valid prefix only
+    const int64_t c = p.counts[b];
+    if (c < limit) limit = c;
+  }
+  for (int64_t i0 = 0; i0 < limit; i0 += kMergeThreads) {
     const int64_t i = i0 + tid;
     float key = 0.f; int id = 0;
-    const bool ok = i < p.per_query && cand_load(p, b, i, thr, key, id);
+    const bool ok = i < limit && cand_load(p, b, i, thr, key, id);
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (bal) {
       int base = 0;

@@ -160,3 +160,39 @@ def test_import_path_shims(native_lib):
     from performance.mlx_optimized import optimized_batch_similarity_search as f
     import b200vs
     assert A is b200vs.MLXVectorStore and f is b200vs.ops.optimized_batch_similarity_search
+
+
+def test_http_shim_replays_reference_integration_test(tmp_path, native_lib):
+    """The reference's tests/test_integration.py:46-160 flow against the /vectors shim:
+    add 100 x 384, count == 100, query with row 0 -> 5 results, rank-1 is doc_0 with
+    similarity > 0.999, filtered query finds exactly the matching document; plus the batched
+    route the reference cannot serve."""
+    from fastapi.testclient import TestClient
+    from b200vs.api_shim import create_app
+    app = create_app(str(tmp_path / "stores"), dimension=384, persist=False, max_vectors=10000)
+    client = TestClient(app)
+    rng = np.random.default_rng(0)
+    vecs = rng.random((100, 384), dtype=np.float32)
+    meta = [{"id": f"doc_{i}", "content_hash": f"hash_{i}"} for i in range(100)]
+    body = {"user_id": "u", "model_id": "m"}
+    r = client.post("/vectors/add", json={**body, "vectors": vecs.tolist(), "metadata": meta})
+    assert r.status_code == 200 and r.json()["vectors_added"] == 100 and r.json()["total_vectors"] == 100
+    r = client.get("/vectors/count", params=body)
+    assert r.json()["count"] == 100                                             # :110
+    r = client.post("/vectors/query", json={**body, "query": vecs[0].tolist(), "k": 5})
+    res = r.json()["results"]
+    assert r.status_code == 200 and len(res) == 5                               # :133
+    assert res[0]["metadata"]["id"] == "doc_0" and res[0]["similarity_score"] > 0.999   # :134-136
+    assert [x["rank"] for x in res] == [1, 2, 3, 4, 5]
+    r = client.post("/vectors/query", json={**body, "query": vecs[10].tolist(), "k": 1,
+                                            "filter_metadata": {"content_hash": "hash_10"}})
+    res = r.json()["results"]
+    assert len(res) == 1 and res[0]["metadata"]["id"] == "doc_10"               # :158-160
+    r = client.post("/vectors/batch_query", json={**body, "queries": vecs[:7].tolist(), "k": 3})
+    out = r.json()
+    assert r.status_code == 200 and out["total_queries"] == 7
+    assert [q[0]["metadata"]["id"] for q in out["results"]] == [f"doc_{i}" for i in range(7)]
+    assert all(len(q) == 3 and q[0]["similarity_score"] > 0.999 for q in out["results"])
+    r = client.post("/vectors/add", json={**body, "vectors": vecs[:2].tolist(), "metadata": meta[:1]})
+    assert r.status_code == 422                                                  # schema validation
+    app.state.store_manager.close()

@@ -117,6 +117,10 @@ class ShardedVectorStore:
         self.shard = factory(dimension, metric, device, shadow_bf16, max_vectors_per_shard, search_mode)
         self.total = 0
         self._bufs = {}
+        # B200VS_SHARD_SYNC=1: synchronise the stream before returning (measured: no effect on throughput)
+        import os
+        self.sync_each_search = (self.world > 1 and device.type == "cuda" and
+                                 os.environ.get("B200VS_SHARD_SYNC", "0") == "1")
 
     # ------------------------------------------------------------------ add
     def add_vectors(self, vectors) -> dict:
@@ -169,7 +173,10 @@ class ShardedVectorStore:
         if self.world == 1:
             return pack[1].clone(), pack[0].view(torch.float32).clone()
         dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
-        return self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
+        out = self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
+        if self.sync_each_search:
+            torch.cuda.current_stream(self.device).synchronize()
+        return out
 
     def close(self) -> None:
         self.shard.close()

@@ -28,14 +28,21 @@ static std::mutex g_prof_mu;
 struct ProfPair { cudaEvent_t a, b; };
 static std::vector<ProfPair> g_prof[kProfKinds];
 
+static std::vector<ProfPair> g_prof_pool;   // recycled event pairs (creating events costs host time)
+
 ProfScope::ProfScope(int kind, cudaStream_t stream) : stream_(stream) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   ProfPair p;
-  if (cudaEventCreate(&p.a) != cudaSuccess) return;
-  if (cudaEventCreate(&p.b) != cudaSuccess) { cudaEventDestroy(p.a); return; }
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (!g_prof_pool.empty()) {
+    p = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else {
+    if (cudaEventCreate(&p.a) != cudaSuccess) return;
+    if (cudaEventCreate(&p.b) != cudaSuccess) { cudaEventDestroy(p.a); return; }
+  }
   cudaEventRecord(p.a, stream);
   stop_ = p.b;
-  std::lock_guard<std::mutex> g(g_prof_mu);
   g_prof[kind].push_back(p);
 }
 ProfScope::~ProfScope() {
@@ -398,8 +405,7 @@ int vs_profile_read(int kind, double* total_ms, int64_t* launches) {
       sum += ms;
       ++n;
     }
-    cudaEventDestroy(p.a);
-    cudaEventDestroy(p.b);
+    g_prof_pool.push_back(p);
   }
   cudaGetLastError();
   g_prof[kind].clear();

@@ -149,3 +149,25 @@ def test_gemm_duplicates_and_self_match(make_store):
     ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "cosine")
     rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
     assert rep.ok, f"{rep}"
+
+
+def test_gemm_mass_ties_fall_back_to_exact_order(make_store):
+    """200 identical rows that all match the query exactly: no 16-bit margin can certify the
+    top-10 among them, so the query must take the retry / exact-scan fallback and still return
+    the ten lowest ids (stable order), while ordinary queries in the same batch stay on K3."""
+    from b200vs import _cabi
+    n, d, B, k = 70000, 128, 64, 10
+    db = datasets.make_db(n, d)
+    dup = np.sort(np.random.default_rng(9).choice(n, 200, replace=False))
+    db[dup] = db[dup[0]]
+    q = datasets.make_queries(B, d)
+    q[5] = db[dup[0]]
+    st = make_store(d, "cosine")
+    st.add_vectors(db, [])
+    ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["gemm"])
+    assert ids[5].tolist() == dup[:10].tolist()
+    assert np.allclose(scores[5], 1.0, atol=1e-6)
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "cosine")
+    rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
+    assert rep.ok, f"{rep}"
+    assert int(_cabi.lib().vs_fallback_count(st._handle)) >= 1

@@ -196,3 +196,58 @@ def test_http_shim_replays_reference_integration_test(tmp_path, native_lib):
     r = client.post("/vectors/add", json={**body, "vectors": vecs[:2].tolist(), "metadata": meta[:1]})
     assert r.status_code == 422                                                  # schema validation
     app.state.store_manager.close()
+
+
+def test_concurrent_queries_during_appends(make_store):
+    """Threading contract of the reference: `query` takes no lock and may run while
+    one `add_vectors` is in flight (api/routes/vectors.py:43 serves both from a 4-thread pool).
+    Every result must be consistent with SOME prefix of the appended rows: ids below the row
+    count seen after the call, sorted scores, and the planted best match once it is visible."""
+    import threading
+    d, chunk, chunks = 128, 5000, 24
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((chunk * chunks, d)).astype(np.float32)
+    probe = rng.standard_normal(d).astype(np.float32)
+    planted_at = chunk * 10 + 17
+    base[planted_at] = probe * 3.0                       # cosine 1.0 with the probe
+    st = make_store(d)
+    st.add_vectors(base[:chunk], [{} for _ in range(chunk)])
+    errors, seen_planted = [], []
+    stop = threading.Event()
+
+    def reader(batch):
+        q = np.tile(probe, (batch, 1)) if batch > 1 else probe
+        while not stop.is_set():
+            try:
+                if batch == 1:
+                    ids, scores, _ = st.query(q, k=5)
+                    res = [(ids, scores)]
+                else:
+                    res = [(i, s) for i, s, _ in st.batch_query(q, k=5)]
+                n_after = st.get_stats()["vector_count"]
+                for ids, scores in res:
+                    assert len(ids) == 5 and all(0 <= i < n_after for i in ids), (ids, n_after)
+                    assert all(a >= b for a, b in zip(scores, scores[1:]))
+                    if ids[0] == planted_at:
+                        assert scores[0] > 0.9999
+                        seen_planted.append(True)
+                    else:
+                        assert scores[0] < 0.9          # random rows are far from the probe
+            except Exception as e:                       # noqa: BLE001
+                errors.append(repr(e))
+                stop.set()
+
+    threads = [threading.Thread(target=reader, args=(b,)) for b in (1, 1, 8)]
+    for t in threads:
+        t.start()
+    for c in range(1, chunks):
+        st.add_vectors(base[c * chunk:(c + 1) * chunk], [{} for _ in range(chunk)])
+    import time as _t
+    _t.sleep(0.2)
+    stop.set()
+    for t in threads:
+        t.join(timeout=30)
+    assert not errors, errors[:3]
+    assert seen_planted, "the planted row was never returned after it became visible"
+    ids, _, _ = st.query(probe, k=1)
+    assert ids == [planted_at]

@@ -520,6 +520,8 @@ def run_b200(args):
                                "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
                                "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
                                "scan_fallback_ms_per_step": scan_ms / steps,
+                               # the runs are power-capped (clocks.reasons): the sustained cuBLAS figure
+                               "frac_of_sustained_peak": ach / tc_sust, "sustained_peak": tc_sust,
                                # small batches are HBM-bound on the 16-bit shadow copy they stream
                                "hbm_gbs_of_16bit_rows": float(n_local) * d * 2 / (per_step * 1e-3) / 1e9}
         elif scan_n:

@@ -938,11 +938,16 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   // f = sqrt(1920 kc / N): 8 % at N = 10 M, 22 % at N = 1.25 M (one of 8 shards).  At most 4096
   // tiles (merge kernel capacity), at least 4 kc, whole tiles only.
   double f = std::sqrt(1920.0 * kc / (double)n);
+  // K > 256 (STREAMING): the MMAs of a tile take several times longer than its epilogue, so the
+  // rare path is hidden and the sample only has to keep the survivors (about 1.2 kc / f per
+  // query) within the candidate buffers and K4's capacity: f = kc / 1500.
+  if (kch > 4) f = std::min(f, kc / 1500.0);
   if (f > 0.5) f = 0.5;
-  if (f < 1.0 / 32) f = 1.0 / 32;
-  // Maxima are taken over groups of kMaxGroupTiles tiles; at most 4096 groups (merge kernel
-  // capacity), at least 4 kc groups so that the kc best rows rarely share a group.
-  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, 4 * kc * kMaxGroupTiles),
+  if (f < 1.0 / 128) f = 1.0 / 128;
+  // Maxima are taken over groups of kMaxGroupTiles tiles when there are plenty (at most 4096
+  // groups: merge kernel capacity), else per tile; at least 4 kc groups so that the kc best
+  // rows rarely share one.
+  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, 4 * kc),
                                        4096 * kMaxGroupTiles);
   if (s_tiles > (int)(n / tn)) s_tiles = (int)(n / tn);
   int s_units, s_ngroups, s_lists;

@@ -303,6 +303,46 @@ def config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args):
     return out
 
 
+def fp8_variant(dev, lib, _cabi, ShardedVectorStore, args):
+    """fp8 (e4m3) database variant: K3 with kind::f8f6f4 MMAs over the e4m3 shadow + fp32 rescoring
+    of 4x over-fetched candidates; reported as recall@10 against the engine's exact results."""
+    import torch
+    out = {"workload": "fp8 (e4m3) database variant, cosine top-10: recall@10 vs the exact path and QPS"}
+    for name, batches in (("1Mx1536", (1024, 32)), ("10Mx128", (1024, 32))):
+        n, d = WORKLOADS[name]
+        st = ShardedVectorStore(d, "cosine", device=dev, shadow_bf16=3, max_vectors_per_shard=n + 16,
+                                search_mode="auto")
+        for b in range(N_BLOCKS):
+            g = torch.Generator(device=dev).manual_seed(DB_SEED + b)
+            rows = torch.randn((n // N_BLOCKS, d), generator=g, device=dev, dtype=torch.float32)
+            st.shard.append(rows, b * (n // N_BLOCKS))
+            del rows
+        st.total = n
+        for B in batches:
+            q = torch.randn((B, d), generator=torch.Generator().manual_seed(QUERY_SEED), dtype=torch.float32).to(dev)
+            st.shard.flags = _cabi.SEARCH_MODES["auto"]
+            ref, _ = st.search(q, args.k)
+            st.shard.flags = _cabi.SEARCH_MODES["gemm_fp8"]
+            got, _ = st.search(q, args.k)
+            r, g_ = ref.cpu().numpy(), got.cpu().numpy()
+            hits = sum(len(set(a.tolist()) & set(b_.tolist())) for a, b_ in zip(r, g_))
+            for _ in range(3):
+                st.search(q, args.k)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 20
+            e0.record()
+            for _ in range(steps):
+                st.search(q, args.k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[f"{name} batch {B}"] = {"recall_at_10": hits / r.size, "qps": B / (ms * 1e-3), "ms_per_step": ms}
+        st.close()
+        torch.cuda.empty_cache()
+    return out
+
+
 def k1_append_throughput(dev, lib, _cabi, ShardedVectorStore, args):
     """K1 append_norm alone: device-resident rows appended into a fresh store; bytes = rows read
     + fp32 master written + 16-bit shadow written + norms (HBM-bound copy-like kernel)."""
@@ -618,6 +658,7 @@ def run_b200(args):
         extras.append(config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args))
         extras.append(config_e_streaming(dev, lib, _cabi, ShardedVectorStore, args))
         extras.append(k1_append_throughput(dev, lib, _cabi, ShardedVectorStore, args))
+        extras.append(fp8_variant(dev, lib, _cabi, ShardedVectorStore, args))
     else:
         st.close()
 

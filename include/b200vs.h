@@ -48,7 +48,8 @@ extern "C" {
 
 /* shadow copy of the database scanned by the low-precision candidate kernels */
 #define VS_SHADOW_NONE  0
-#define VS_SHADOW_BF16  1
+#define VS_SHADOW_BF16  1   /* 16-bit copy: fp16 of x/||x|| for cosine, bf16 of x otherwise            */
+#define VS_SHADOW_FP8   2   /* additional e4m3 copy (cosine only) for VS_SEARCH_GEMM_FP8; may be OR-ed */
 
 /* search flags */
 #define VS_SEARCH_AUTO        0   /* choose by batch size                                   */
@@ -57,6 +58,8 @@ extern "C" {
 #define VS_SEARCH_GEMM        3   /* K3: tcgen05 bf16 GEMM candidates + K5 rescoring,
                                      certified exact with fp32 fallback                      */
 #define VS_SEARCH_GEMM_NOCERT 4   /* K3 + K5 without certification (recall reported)        */
+#define VS_SEARCH_GEMM_FP8    5   /* K3 over the e4m3 shadow (kind::f8f6f4) + K5 rescoring; no
+                                     certification: recall-reported variant                  */
 #define VS_SEARCH_MODE_MASK   0xff
 #define VS_SEARCH_TMA         0x100  /* K2 variant: cp.async.bulk (TMA) staged tiles        */
 #define VS_SEARCH_LDG         0x200  /* K2 variant: direct 128-bit global loads             */

@@ -17,11 +17,11 @@ HEADER = PKG_DIR.parent.parent / "include" / "b200vs.h"
 VS_OK, VS_ERR_INVALID, VS_ERR_CUDA, VS_ERR_OOM, VS_ERR_STATE = 0, 1, 2, 3, 4
 METRIC_COSINE, METRIC_EUCLIDEAN, METRIC_DOT = 0, 1, 2
 METRICS = {"cosine": METRIC_COSINE, "euclidean": METRIC_EUCLIDEAN, "dot_product": METRIC_DOT}
-SHADOW_NONE, SHADOW_BF16 = 0, 1
-SEARCH_AUTO, SEARCH_SCAN_FP32, SEARCH_SCAN_BF16, SEARCH_GEMM, SEARCH_GEMM_NOCERT = 0, 1, 2, 3, 4
+SHADOW_NONE, SHADOW_BF16, SHADOW_FP8 = 0, 1, 2
+SEARCH_AUTO, SEARCH_SCAN_FP32, SEARCH_SCAN_BF16, SEARCH_GEMM, SEARCH_GEMM_NOCERT, SEARCH_GEMM_FP8 = 0, 1, 2, 3, 4, 5
 SEARCH_TMA, SEARCH_LDG = 0x100, 0x200
 SEARCH_MODES = {"auto": SEARCH_AUTO, "scan_fp32": SEARCH_SCAN_FP32, "scan_bf16": SEARCH_SCAN_BF16,
-                "gemm": SEARCH_GEMM, "gemm_nocert": SEARCH_GEMM_NOCERT}
+                "gemm": SEARCH_GEMM, "gemm_nocert": SEARCH_GEMM_NOCERT, "gemm_fp8": SEARCH_GEMM_FP8}
 
 _lib = None
 

@@ -34,7 +34,7 @@ class NativeShard:
         self.flags = _cabi.SEARCH_MODES[search_mode]
         self.handle = C.c_void_p()
         _cabi.check(_cabi.lib().vs_create(device.index or 0, dimension, self.metric,
-                                          _cabi.SHADOW_BF16 if shadow_bf16 else _cabi.SHADOW_NONE,
+                                          int(shadow_bf16),      # bool, or a VS_SHADOW_* mask
                                           int(max_vectors), C.byref(self.handle)))
 
     def _stream(self):

@@ -40,7 +40,8 @@ class MLXVectorStoreConfig:
     jit_compile: bool = True
     # --- engine extensions (not in the reference) ---
     device: int = 0
-    shadow_bf16: bool = True      # keep a bf16 copy for the tensor-core candidate kernels
+    shadow_bf16: bool = True      # keep a 16-bit copy for the tensor-core candidate kernels
+    shadow_fp8: bool = False      # additionally keep an e4m3 copy (cosine; search_mode "gemm_fp8")
     max_vectors: int = 0          # address-space reservation; 0 = derive from device memory
     search_mode: str = "auto"     # auto | scan_fp32 | scan_bf16 | gemm | gemm_nocert
     persist: bool = True          # write appended rows to disk on every add (reference does)
@@ -83,7 +84,8 @@ class MLXVectorStore:
         metric = self._metric_id if self._metric_id is not None else _cabi.METRIC_COSINE
         _cabi.check(_cabi.lib().vs_create(
             int(self.config.device), int(self.config.dimension), metric,
-            _cabi.SHADOW_BF16 if self.config.shadow_bf16 else _cabi.SHADOW_NONE,
+            (_cabi.SHADOW_BF16 if self.config.shadow_bf16 else 0) |
+            (_cabi.SHADOW_FP8 if self.config.shadow_fp8 else 0),
             int(self.config.max_vectors), C.byref(self._handle)))
 
     def close(self):

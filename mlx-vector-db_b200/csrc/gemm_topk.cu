@@ -29,6 +29,7 @@
 //     step; database tiles of 256 rows; 2 TMEM accumulators of 256 columns.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cmath>
@@ -66,6 +67,7 @@ struct GemmParams {
   int nq;                   // live queries
   int mode;
   int fp16;                 // operands are fp16 (cosine) instead of bf16
+  int fp8;                  // operands are e4m3: tcgen05.mma kind::f8f6f4 (K = 32 per MMA, 128 per chunk)
   int stages;               // ring depth
   uint32_t idesc;           // tcgen05 instruction descriptor (operand format, M, N)
   const float* tau;         // (nq,) filter threshold (kModeFilter)
@@ -123,6 +125,14 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
@@ -185,6 +195,9 @@ template <> struct CgOps<1> {
   __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     tc_mma(d, a, b, idesc, acc);
   }
+  __device__ static __forceinline__ void mma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    tc_mma_f8(d, a, b, idesc, acc);
+  }
   __device__ static __forceinline__ void commit(uint32_t bar) { tc_commit(bar); }
   __device__ static __forceinline__ void load(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     tma_load_2d(dst, map, c0, c1, bar);
@@ -203,6 +216,13 @@ template <> struct CgOps<2> {
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  }
+  __device__ static __forceinline__ void mma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
   }
   // arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair
@@ -251,6 +271,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   unsigned char* smem = smem_raw + ((1024 - (s_u32(smem_raw) & 1023)) & 1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kch = p.kchunks;
+  const int kstep = p.fp8 ? 128 : kChunkK;                // elements per 128-byte chunk row
   const int crank = CG == 2 ? (int)cluster_rank() : 0;    // 0 = leader (issues the MMAs)
 
   // ---- carve-up
@@ -304,7 +325,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (crank == 0) bar_expect_tx(bar_a, (uint32_t)(CG * m_count * kch * kChunkBytes));
         for (int mt = 0; mt < m_count; ++mt)
           for (int kc = 0; kc < kch; ++kc)
-            Ops::load(s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes), &map_q, kc * kChunkK,
+            Ops::load(s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes), &map_q, kc * kstep,
                       ((m_first + mt) * CG + crank) * kTileM, bar_a);
       }
       int st = 0;
@@ -317,8 +338,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           if (crank == 0) bar_expect_tx(bar_full + 8 * st, (uint32_t)(CG * kch * B_CHUNK_BYTES));
           for (int kc = 0; kc < kch; ++kc) {
             unsigned char* dst = ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES;
-            Ops::load(s_u32(dst), &map_x, kc * kChunkK, row0, bar_full + 8 * st);
-            if (TN_LOCAL == 256) Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kChunkK, row0 + 128, bar_full + 8 * st);
+            Ops::load(s_u32(dst), &map_x, kc * kstep, row0, bar_full + 8 * st);
+            if (TN_LOCAL == 256) Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kstep, row0 + 128, bar_full + 8 * st);
           }
           if (++st == p.stages) { st = 0; ph ^= 1u; }
         } else {
@@ -327,10 +348,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               bar_wait(bar_empty + 8 * st, ph ^ 1u);
               if (crank == 0) bar_expect_tx(bar_full + 8 * st, (uint32_t)(CG * (kChunkBytes + B_CHUNK_BYTES)));
               unsigned char* dst = ring + (size_t)st * stage_bytes;
-              Ops::load(s_u32(dst), &map_q, kc * kChunkK, (mt * CG + crank) * kTileM, bar_full + 8 * st);
-              Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kChunkK, row0, bar_full + 8 * st);
+              Ops::load(s_u32(dst), &map_q, kc * kstep, (mt * CG + crank) * kTileM, bar_full + 8 * st);
+              Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kstep, row0, bar_full + 8 * st);
               if (TN_LOCAL == 256)   // 256 rows = two boxes of 128
-                Ops::load(s_u32(dst + 2 * kChunkBytes), &map_x, kc * kChunkK, row0 + 128, bar_full + 8 * st);
+                Ops::load(s_u32(dst + 2 * kChunkBytes), &map_x, kc * kstep, row0 + 128, bar_full + 8 * st);
               if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
@@ -368,10 +389,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             const uint64_t a_desc = smem_desc(a_addr);
             const uint64_t b_desc = smem_desc(b_addr);
+            if (p.fp8) {
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k)      // +32 B per 16-element K step
-              Ops::mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                       (kc | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)               // e4m3: +32 B per 32-element K step
+                Ops::mma_f8(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                            (kc | k) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k)    // 16-bit: +32 B per 16-element K step
+                Ops::mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                         (kc | k) != 0 ? 1u : 0u);
+            }
             if (!RES) {
               Ops::commit(bar_empty + 8 * st);          // smem stage free once these MMAs retire
               if (++st == p.stages) { st = 0; ph ^= 1u; }
@@ -588,6 +616,25 @@ __global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int
   if (lane == 0) { qerr[b] = sqrtf(e2) * 1.00001f; qlen[b] = sqrtf(u2) * 1.00001f; }
 }
 
+// queries -> e4m3 of 16 * q / max(||q||, 1e-8), padded to (rows_padded, ld8)
+__global__ void prep_queries_fp8_kernel(const float* __restrict__ q, int B, int dim, int ld8, int rows_padded,
+                                        unsigned char* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= rows_padded) return;
+  unsigned char* dst = out + (size_t)b * ld8;
+  if (b >= B) {
+    for (int c = lane; c < ld8; c += 32) dst[c] = 0;
+    return;
+  }
+  const float* src = q + (size_t)b * dim;
+  float acc = 0.f;
+  for (int c = lane; c < dim; c += 32) { const float v = src[c]; acc = fmaf(v, v, acc); }
+  const float sc = 16.f / fmaxf(sqrtf(warp_sum(acc)), 1e-8f);
+  for (int c = lane; c < ld8; c += 32)
+    dst[c] = (unsigned char)__nv_cvt_float_to_fp8(c < dim ? src[c] * sc : 0.f, __NV_SATFINITE, __NV_E4M3);
+}
+
 // K5 + final K4 + certification in one launch: one CTA per query.
 //   warp 0 prepares the query exactly like prep_queries_kernel (so the scores below are bit-
 //   identical to K2's), the 8 warps rescore the kc candidates in exact fp32 with K2's
@@ -731,14 +778,18 @@ static EncodeTiledFn encode_fn() {
 }
 
 // (rows, K) bf16 row-major matrix, boxes of 128 rows x 64 elements, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, bool fp16) {
+// fmt: 0 = bf16, 1 = fp16, 2 = e4m3 (one byte per element, 128 elements per chunk row)
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int fmt) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VS_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kChunkK, 128};
+  const int esz = fmt == 2 ? 1 : 2;
+  cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  const CUtensorMapDataType dt = fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : (fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return VS_ERR_CUDA; }
@@ -920,10 +971,11 @@ int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bo
 // kc_want: candidates kept for rescoring (0 = default for kk); a query that cannot be certified
 // is retried once with 4x the candidates (a wider bf16 margin) before the exact scan takes it
 static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
-                      float* out_scores, int32_t* out_ids, int64_t out_stride, int kc_want,
+                      float* out_scores, int32_t* out_ids, int64_t out_stride, int kc_want, bool fp8,
                       cudaStream_t stream) {
-  const int K = s->ld16;
-  const int kch = K / kChunkK;
+  // fp8: e4m3 shadow, 128 elements per 128-byte chunk row; otherwise the 16-bit shadow, 64 per row
+  const int K = fp8 ? s->ld8 : s->ld16;
+  const int kch = fp8 ? K / 128 : K / kChunkK;
   const int cg = gemm_cta_group(kch);
   const int m_tiles = ((B + kTileM * cg - 1) / (kTileM * cg)) * cg;     // a multiple of cg
   const int rows_padded = m_tiles * kTileM;
@@ -981,16 +1033,21 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
 
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
-  if (int rc = make_map(&mq, qb, rows_padded, K, fp16)) return rc;
-  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16)) return rc;
+  const int fmt = fp8 ? 2 : (fp16 ? 1 : 0);
+  if (int rc = make_map(&mq, qb, rows_padded, K, fmt)) return rc;
+  if (int rc = make_map(&mx, fp8 ? s->shadow8_rows.ptr() : s->shadow_rows.ptr(), n, K, fmt)) return rc;
 
-  prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
-                                                                    qerr, qlen);
+  if (fp8)   // (the buffer is sized for 2 bytes per element; e4m3 uses half of it)
+    prep_queries_fp8_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, K, rows_padded,
+                                                                     reinterpret_cast<unsigned char*>(qb));
+  else
+    prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
+                                                                      qerr, qlen);
   count_launch();
   VS_CHECK_LAUNCH();
 
   GemmParams p = {};
-  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = fp16 ? 1 : 0;
+  p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = (fp16 || fp8) ? 1 : 0; p.fp8 = fp8 ? 1 : 0;
   p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
   p.glist_s = gls; p.glist_i = gli; p.gcount = gcnt;
 
@@ -1053,7 +1110,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   const int kc_retry = std::min(4 * kc, kMaxCand);
   if (kc_want == 0 && kc_retry > kc && (int64_t)kc_retry * 8 <= n) {
     s->retries.fetch_add(h_bad);
-    rc = gemm_block(s, n, gq, h_bad, kk, true, scan_tma, ts, ti, kk, kc_retry, stream);
+    rc = gemm_block(s, n, gq, h_bad, kk, true, scan_tma, ts, ti, kk, kc_retry, false, stream);
   } else {
     s->fallbacks.fetch_add(h_bad);
     rc = scan_queries_exact(s, n, gq, h_bad, kk, scan_tma, ts, ti, kk, stream);
@@ -1071,16 +1128,21 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   return rc;
 }
 
-int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
+int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma, bool fp8,
               float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
-  if (!s->shadow) { set_error("store was created without a bf16 shadow copy"); return VS_ERR_STATE; }
+  if (fp8) {
+    if (!s->shadow8) { set_error("store was created without an fp8 shadow copy (VS_SHADOW_FP8)"); return VS_ERR_STATE; }
+    certify = false;            // e4m3 rounding is far above any top-k margin: recall-reported variant
+  } else if (!s->shadow) { set_error("store was created without a 16-bit shadow copy"); return VS_ERR_STATE; }
   if (s->metric == VS_METRIC_EUCLIDEAN) { set_error("the GEMM path serves cosine and dot_product"); return VS_ERR_STATE; }
   if (cand_count(kk) > kMaxCand) { set_error("invalid argument: k too large for the GEMM path (k <= 128)"); return VS_ERR_INVALID; }
+  // the fp8 variant keeps 4x the candidates for the exact rescoring
+  const int kc_want = fp8 ? std::min(4 * cand_count(kk), kMaxCand) : 0;
   for (int b0 = 0; b0 < B; b0 += kMaxQueriesPerLaunch) {
     const int nb = std::min(kMaxQueriesPerLaunch, B - b0);
     if (int rc = gemm_block(s, n, q + (size_t)b0 * s->dim, nb, kk, certify, scan_tma,
                             out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride, out_stride,
-                            0, stream))
+                            kc_want, fp8, stream))
       return rc;
   }
   return VS_OK;
@@ -1103,8 +1165,8 @@ int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, 
   if (int rc = ws.alloc(stream)) return rc;
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
-  if (int rc = make_map(&mq, qb, rows_padded, K, fp16)) return rc;
-  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16)) return rc;
+  if (int rc = make_map(&mq, qb, rows_padded, K, fp16 ? 1 : 0)) return rc;
+  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16 ? 1 : 0)) return rc;
   prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
                                                                     qerr, qlen);
   count_launch();

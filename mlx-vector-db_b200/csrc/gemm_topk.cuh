@@ -13,7 +13,8 @@ bool gemm_supported(const vs_store* s, int64_t n, int B, int kk);
 // B queries against n rows; results (kk live entries per query) at out_*[b * out_stride].
 // certify: prove per query that the bf16 candidate set contains the exact fp32 top-k, and
 // re-run the queries that cannot be proven through the exact fp32 scan.
-int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
+// fp8: run over the e4m3 shadow (kind::f8f6f4), never certified (recall-reported)
+int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma, bool fp8,
               float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream);
 
 }  // namespace vs

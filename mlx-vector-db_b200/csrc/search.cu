@@ -187,7 +187,10 @@ int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32
     case VS_SEARCH_GEMM:
     case VS_SEARCH_GEMM_NOCERT:
       if (row_mask != nullptr) { set_error("row_mask is not supported by the GEMM path"); return VS_ERR_INVALID; }
-      return gemm_path(s, n, q, B, kk, mode == VS_SEARCH_GEMM, use_tma, out_scores, out_ids, k, stream);
+      return gemm_path(s, n, q, B, kk, mode == VS_SEARCH_GEMM, use_tma, false, out_scores, out_ids, k, stream);
+    case VS_SEARCH_GEMM_FP8:
+      if (row_mask != nullptr) { set_error("row_mask is not supported by the GEMM path"); return VS_ERR_INVALID; }
+      return gemm_path(s, n, q, B, kk, false, use_tma, true, out_scores, out_ids, k, stream);
     default:
       set_error("invalid argument: unknown search mode");
       return VS_ERR_INVALID;

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "store.cuh"
 
 namespace vs {
@@ -377,6 +378,31 @@ append_norm_kernel(const float* __restrict__ src, int64_t src_ld, float* __restr
   }
 }
 
+// e4m3 shadow rows for the fp8 GEMM candidates: 16 * x / max(||x||, 1e-8) (the factor 16 keeps
+// unit-norm components of D up to a few thousand inside e4m3's normal range), 4 elements per lane
+__global__ void __launch_bounds__(256)
+shadow8_kernel(const float* __restrict__ rows, int ld, int dim, const float* __restrict__ norms, int64_t n0,
+               int64_t m, unsigned char* __restrict__ out, int ld8) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < m; r += nwarps) {
+    const float* x = rows + (n0 + r) * (int64_t)ld;
+    const float sc = 16.f / norms[n0 + r];
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + (n0 + r) * (int64_t)ld8);
+    for (int c4 = lane; c4 < (ld8 >> 2); c4 += 32) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 4 * c4 + j;
+        const float v = c < dim ? x[c] * sc : 0.f;
+        w |= (uint32_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3) << (8 * j);
+      }
+      o[c4] = w;
+    }
+  }
+}
+
 }  // namespace vs
 
 using namespace vs;
@@ -419,7 +445,8 @@ int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_
   *out = nullptr;
   VS_REQUIRE(dim > 0 && dim <= 65536, "dim must be in [1, 65536]");
   VS_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (cosine), 1 (euclidean) or 2 (dot)");
-  VS_REQUIRE(shadow == VS_SHADOW_NONE || shadow == VS_SHADOW_BF16, "shadow must be 0 or 1");
+  VS_REQUIRE(shadow >= 0 && shadow <= (VS_SHADOW_BF16 | VS_SHADOW_FP8), "shadow must be a VS_SHADOW_* mask");
+  VS_REQUIRE(!(shadow & VS_SHADOW_FP8) || metric == VS_METRIC_COSINE, "the fp8 shadow copy serves cosine only");
   VS_REQUIRE(max_rows >= 0 && max_rows < (int64_t)0x7fffffff, "max_rows must be < 2^31");
   int ndev = 0;
   VS_CUDA(cudaGetDeviceCount(&ndev));
@@ -438,9 +465,12 @@ int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_
   s->ld = (int)round_up(dim, 4);
   s->ld16 = (int)round_up(dim, 64);
   s->metric = metric;
-  s->shadow = shadow;
+  s->shadow = (shadow & VS_SHADOW_BF16) ? 1 : 0;
+  s->shadow8 = (shadow & VS_SHADOW_FP8) ? 1 : 0;
+  s->ld8 = (int)round_up(dim, 128);
+  shadow = s->shadow;
   s->num_sms = prop.multiProcessorCount;
-  const size_t row_bytes = (size_t)s->ld * 4 + 8 + (shadow ? (size_t)s->ld16 * 2 : 0);
+  const size_t row_bytes = (size_t)s->ld * 4 + 8 + (shadow ? (size_t)s->ld16 * 2 : 0) + (s->shadow8 ? s->ld8 : 0);
   if (max_rows == 0) {
     max_rows = (int64_t)((double)prop.totalGlobalMem * 0.92 / (double)row_bytes);
     if (max_rows > 0x7ffffff0) max_rows = 0x7ffffff0;
@@ -450,6 +480,7 @@ int vs_create(int device, int dim, int metric, int shadow, int64_t max_rows, vs_
   if (!rc) rc = s->norms.init(device, (size_t)max_rows * 4 + 64);
   if (!rc) rc = s->sqnorms.init(device, (size_t)max_rows * 4);
   if (!rc && shadow) rc = s->shadow_rows.init(device, (size_t)max_rows * s->ld16 * 2);
+  if (!rc && s->shadow8) rc = s->shadow8_rows.init(device, (size_t)max_rows * s->ld8);
   if (!rc) rc = s->gids.init(device, (size_t)max_rows * 4);
   if (rc) { vs_destroy(s); return rc; }
   // keep stream-ordered workspace memory cached in the pool between searches
@@ -479,6 +510,7 @@ int vs_destroy(vs_store* s) {
   s->norms.destroy();
   s->sqnorms.destroy();
   s->shadow_rows.destroy();
+  s->shadow8_rows.destroy();
   s->gids.destroy();
   if (s->bounds) cudaFree(s->bounds);
   if (s->append_done) cudaEventDestroy(s->append_done);
@@ -497,7 +529,7 @@ int64_t vs_retry_count(const vs_store* s) { return s ? s->retries.load() : 0; }
 int64_t vs_memory_bytes(const vs_store* s) {
   if (!s) return 0;
   return (int64_t)(s->rows.mapped() + s->norms.mapped() + s->sqnorms.mapped() +
-                   s->shadow_rows.mapped() + s->gids.mapped());
+                   s->shadow_rows.mapped() + s->shadow8_rows.mapped() + s->gids.mapped());
 }
 
 int vs_reset(vs_store* s) {
@@ -533,6 +565,8 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
   if (int rc = s->sqnorms.ensure((size_t)n1 * 4, stream)) return rc;
   if (s->shadow)
     if (int rc = s->shadow_rows.ensure((size_t)n1 * s->ld16 * 2, stream)) return rc;
+  if (s->shadow8)
+    if (int rc = s->shadow8_rows.ensure((size_t)n1 * s->ld8, stream)) return rc;
   const bool with_ids = first_global_id >= 0;
   if (s->mapped && !with_ids) {
     set_error("store maps local rows to global ids: append with vs_append_ids");
@@ -589,6 +623,13 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
         s->bounds);
     count_launch();
     VS_CHECK_LAUNCH();
+    if (s->shadow8) {
+      shadow8_kernel<<<(unsigned)std::min<int64_t>((mm + 7) / 8, cap), 256, 0, stream>>>(
+          master, s->ld, s->dim, (const float*)s->norms.ptr(), n0 + off, mm,
+          (unsigned char*)s->shadow8_rows.ptr(), s->ld8);
+      count_launch();
+      VS_CHECK_LAUNCH();
+    }
     if (staging) VS_CUDA(cudaFreeAsync(staging, stream));
   }
   if (!rows_on_device) VS_CUDA(cudaStreamSynchronize(stream));  // host buffer may be reused

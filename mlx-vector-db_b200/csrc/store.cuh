@@ -35,7 +35,9 @@ struct vs_store {
   int device = 0;
   int dim = 0;        // D
   int ld = 0;         // fp32 row stride in floats (D rounded up to 4 -> 16 B aligned rows)
-  int ld16 = 0;       // bf16 shadow row stride in elements (D rounded up to 64 -> 128 B)
+  int ld16 = 0;       // 16-bit shadow row stride in elements (D rounded up to 64 -> 128 B)
+  int ld8 = 0;        // fp8 shadow row stride in elements = bytes (D rounded up to 128)
+  int shadow8 = 0;    // keep an e4m3 shadow copy (cosine only): 16 * x/||x||, recall-reported searches
   int metric = 0;
   int shadow = 0;
   int num_sms = 148;
@@ -55,7 +57,8 @@ struct vs_store {
   vs::Arena rows;                // fp32 master, (N, ld)
   vs::Arena norms;               // max(||x||, 1e-8), (N,)
   vs::Arena sqnorms;             // ||x||^2, (N,)
-  vs::Arena shadow_rows;         // bf16, (N, ld16): x/max(||x||,1e-8) for cosine, x otherwise
+  vs::Arena shadow_rows;         // 16-bit, (N, ld16): fp16 of x/max(||x||,1e-8) for cosine, bf16 of x otherwise
+  vs::Arena shadow8_rows;        // e4m3, (N, ld8): 16 * x/max(||x||,1e-8)
   uint32_t* bounds = nullptr;    // device: float bits of max ||v - bf16(v)||, max ||bf16(v)||
   vs::Arena gids;                // int32 global id per local row (row-sharded stores only)
   bool mapped = false;           // true once an append supplied global ids

@@ -171,3 +171,38 @@ def test_gemm_mass_ties_fall_back_to_exact_order(make_store):
     rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
     assert rep.ok, f"{rep}"
     assert int(_cabi.lib().vs_fallback_count(st._handle)) >= 1
+
+
+@pytest.mark.parametrize("shape", [(100000, 128, 256, 10), (70000, 768, 64, 10), (80000, 1536, 130, 10)],
+                         ids=["N100000_D128", "N70000_D768", "N80000_D1536"])
+def test_fp8_database_recall_with_fp32_rescoring(make_store, shape):
+    """fp8 (e4m3) database variant: K3 with tcgen05.mma kind::f8f6f4 over the e4m3 shadow copy,
+    4x over-fetched candidates rescored in exact fp32.  Not certified: reported as recall@k
+    against the oracle ids (BASELINE.json); rescored scores are the exact fp32 ones."""
+    from b200vs import _cabi
+    n, d, B, k = shape
+    db = datasets.make_db(n, d)
+    q = datasets.make_queries(B, d)
+    st = make_store(d, "cosine", shadow_fp8=True)
+    st.add_vectors(db, [])
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "cosine")
+    ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["gemm_fp8"])
+    rec = compare.recall_at_k(ref_ids, ids)
+    assert rec >= 0.99, rec
+    got = np.take_along_axis(S, ids.astype(np.int64), axis=1)
+    np.testing.assert_allclose(scores, got, atol=1e-5)
+    assert (np.diff(scores, axis=1) <= 0).all()
+    # the exact modes are untouched by the extra shadow copy
+    ids2, scores2 = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["gemm"])
+    rep = compare.compare_topk(ref_ids, ref_scores, ids2, scores2, S)
+    assert rep.ok, f"{rep}"
+
+
+def test_fp8_mode_needs_the_fp8_shadow(make_store):
+    from b200vs import _cabi
+    st = make_store(128, "cosine")
+    st.add_vectors(datasets.make_db(70000, 128), [])
+    with pytest.raises(RuntimeError):
+        st.search_arrays(datasets.make_queries(4, 128), 10, flags=_cabi.SEARCH_MODES["gemm_fp8"])
+    with pytest.raises(ValueError):
+        make_store(128, "euclidean", shadow_fp8=True)

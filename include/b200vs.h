@@ -52,11 +52,14 @@ extern "C" {
 #define VS_SHADOW_FP8   2   /* additional e4m3 copy (cosine only) for VS_SEARCH_GEMM_FP8; may be OR-ed */
 
 /* search flags */
-#define VS_SEARCH_AUTO        0   /* choose by batch size                                   */
+#define VS_SEARCH_AUTO        0   /* one query: K2 fp32 scan; two or more: K3 (when the store
+                                     has the 16-bit shadow, cosine / dot_product, k <= 128,
+                                     >= 65536 rows, no row mask), else K2                    */
 #define VS_SEARCH_SCAN_FP32   1   /* K2: fp32 streaming scan (exact)                        */
-#define VS_SEARCH_SCAN_BF16   2   /* K2 over the bf16 shadow + K5 fp32 rescoring (recall)   */
-#define VS_SEARCH_GEMM        3   /* K3: tcgen05 bf16 GEMM candidates + K5 rescoring,
-                                     certified exact with fp32 fallback                      */
+#define VS_SEARCH_SCAN_BF16   2   /* K2 over the 16-bit shadow + K5 fp32 rescoring (recall) */
+#define VS_SEARCH_GEMM        3   /* K3: tcgen05 16-bit GEMM candidates + K5 rescoring,
+                                     certified exact; uncertified queries are retried with 4x
+                                     the candidates, then re-run through the exact scan      */
 #define VS_SEARCH_GEMM_NOCERT 4   /* K3 + K5 without certification (recall reported)        */
 #define VS_SEARCH_GEMM_FP8    5   /* K3 over the e4m3 shadow (kind::f8f6f4) + K5 rescoring; no
                                      certification: recall-reported variant                  */
@@ -92,7 +95,7 @@ VS_API int vs_destroy(vs_store* s);
 /* K1 append_norm -- replaces `mx.concatenate([self._vectors, new])` + `mx.eval`
  * (service/optimized_vector_store.py:98-106) and the per-query re-normalisation of the whole
  * database (:34-38).  Copies `m` rows of `dim` fp32 (row-major, contiguous) to the end of the
- * store, computes max(||x||, 1e-8) and ||x||^2 per row and the optional bf16 shadow.
+ * store, computes max(||x||, 1e-8) and ||x||^2 per row and the optional shadow copies.
  *   rows_on_device: 0 = host pointer (copied by the library), 1 = device pointer.
  * Rows become visible to searches enqueued after this call returns. */
 VS_API int vs_append(vs_store* s, const float* rows, int64_t m, int rows_on_device,
@@ -171,7 +174,7 @@ VS_API int vs_score_matrix(int device, int metric, const float* q, int B, const 
                            int64_t n, int dim, float* out, void* stream);
 
 /* Test hook for K3: the full (B, count) matrix of tensor-core scores
- * bf16(prep(q)) . bf16(shadow row) with fp32 accumulation, exactly what the GEMM path's
+ * half(prep(q)) . half(shadow row) (fp16 for cosine, bf16 otherwise) with fp32 accumulation, exactly what the GEMM path's
  * epilogue filters.  `out` is a (B, count) fp32 DEVICE buffer.  Not used by the search path. */
 VS_API int vs_debug_gemm_scores(vs_store* s, const float* q, int B, float* out, void* stream);
 

@@ -1007,6 +1007,13 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   const int gt = s_tiles / kMaxGroupTiles >= 4 * kc ? kMaxGroupTiles : 1;
   const int s_groups = s_lists * (((s_tiles + s_lists - 1) / s_lists + gt - 1) / gt);
   const bool sampled = s_tiles / gt >= 2 * kc && s_groups <= 4096;
+  // Too few rows for a useful threshold (fewer than 2 kc sample groups): every row would be a
+  // candidate and the per-thread buffers would overflow.  Such a store is small; the exact scan
+  // serves it directly (for the uncertified modes too: its recall is 1).
+  if (!sampled) {
+    s->fallbacks.fetch_add(B);
+    return scan_queries_exact(s, n, q, B, kk, scan_tma, out_scores, out_ids, out_stride, stream);
+  }
 
   const int max_lists = s->num_sms;
   Ws ws;

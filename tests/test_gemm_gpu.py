@@ -206,3 +206,19 @@ def test_fp8_mode_needs_the_fp8_shadow(make_store):
         st.search_arrays(datasets.make_queries(4, 128), 10, flags=_cabi.SEARCH_MODES["gemm_fp8"])
     with pytest.raises(ValueError):
         make_store(128, "euclidean", shadow_fp8=True)
+
+
+def test_gemm_modes_on_a_small_store_use_the_exact_scan(make_store):
+    """Explicit GEMM modes on a store too small for a pass-1 threshold must still answer
+    correctly (they hand the batch to the exact scan)."""
+    from b200vs import _cabi
+    n, d, B, k = 3000, 128, 40, 10
+    db = datasets.make_db(n, d)
+    q = datasets.make_queries(B, d)
+    st = make_store(d, "cosine", shadow_fp8=True)
+    st.add_vectors(db, [])
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "cosine")
+    for mode in ("gemm", "gemm_nocert", "gemm_fp8"):
+        ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES[mode])
+        rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
+        assert rep.ok, (mode, f"{rep}")

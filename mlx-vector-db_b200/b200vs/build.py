@@ -44,7 +44,21 @@ def _digest() -> str:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile (if the sources changed since the last build) and return the library path.
+    Safe to call from several processes at once (one rank per GPU under torchrun): an exclusive
+    file lock serialises the builders, later ones find the stamp up to date, and the library is
+    moved into place atomically so a reader never sees a half-written file."""
+    import fcntl
     BUILD.mkdir(exist_ok=True)
+    with open(BUILD / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     stamp = BUILD / "stamp.txt"
     dig = _digest()
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
@@ -62,11 +76,13 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
+    tmp = LIB.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp),
            *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    os.replace(tmp, LIB)
     stamp.write_text(dig)
     if verbose:
         print(f"built {LIB}")

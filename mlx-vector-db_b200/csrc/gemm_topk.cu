@@ -1017,7 +1017,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
 
   const int max_lists = s->num_sms;
   Ws ws;
-  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *c1s, *rk, *gls; int32_t *ci, *ccnt, *c1i, *ovf, *bad, *gli, *gcnt; int* nbad;
+  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *c1s, *gls; int32_t *ci, *ccnt, *c1i, *ovf, *bad, *gli, *gcnt; int* nbad;
   ws.want(&qb, (size_t)rows_padded * K);
   ws.want(&qerr, (size_t)rows_padded);
   ws.want(&qlen, (size_t)rows_padded);
@@ -1030,7 +1030,6 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   ws.want(&gli, (size_t)rows_padded * kGlobalCap);
   ws.want(&c1s, (size_t)B * kc);
   ws.want(&c1i, (size_t)B * kc);
-  ws.want(&rk, (size_t)B * kc);
   int32_t* zeroed;                       // [overflow | gcount | n_bad], cleared by ONE memset
   ws.want(&zeroed, (size_t)2 * rows_padded + 1);
   ws.want(&bad, (size_t)B);
@@ -1077,10 +1076,9 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
     VS_CHECK_LAUNCH();
   }
   // pass 2: threshold filter over all rows
-  int lists = 0;
   p.mode = kModeFilter; p.n_tiles = n_tiles; p.gmax = nullptr;
-  if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, &lists, stream)) return rc;
-  // K4: best kc candidates by bf16 score
+  if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
+  // K4: best kc candidates by 16-bit (or e4m3) score out of the dense per-query lists
   {
     MergeParams m = {};
     m.ck = gls; m.ci = gli; m.per_query = kGlobalCap; m.chunk = kGlobalCap;

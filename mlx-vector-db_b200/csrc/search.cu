@@ -45,7 +45,7 @@ static bool default_tma() {
   return v == 1;
 }
 
-// K2 path: scan (fp32 master or bf16 shadow) -> merge.  Results for query b land in
+// K2 path: scan (fp32 master or 16-bit shadow) -> merge.  Results for query b land in
 // out_*[b * out_stride ..], kk live entries each.
 static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool bf16,
                      bool use_tma, const uint32_t* row_mask, float* out_scores, int32_t* out_ids,
@@ -171,7 +171,7 @@ int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32
     case VS_SEARCH_SCAN_FP32:
       return scan_path(s, n, q, B, kk, false, use_tma, row_mask, out_scores, out_ids, k, true, stream);
     case VS_SEARCH_SCAN_BF16: {
-      if (!s->shadow) { set_error("store was created without a bf16 shadow copy"); return VS_ERR_STATE; }
+      if (!s->shadow) { set_error("store was created without a 16-bit shadow copy"); return VS_ERR_STATE; }
       // over-fetch, then exact fp32 rescoring of the candidates (K5)
       int kc = (int)std::min<int64_t>(n, std::max(2 * kk, kk + 32));
       if (kc > 1024) kc = (int)std::min<int64_t>(n, 1024);

@@ -25,6 +25,11 @@ NVCC_FLAGS = [
 # tuning knob (diagnostic): B200VS_EPI_GROUPS=4 builds K3 with 16 epilogue warps
 if os.environ.get("B200VS_EPI_GROUPS"):
     NVCC_FLAGS.append("-DVS_EPI_GROUPS=" + os.environ["B200VS_EPI_GROUPS"])
+# diagnostic: B200VS_DEBUG_BUILD=1 adds K3's timing-experiment epilogues (B200VS_GEMM_DBGMODE)
+if os.environ.get("B200VS_RES_TN"):          # diagnostic: K3 RESIDENT tile width (128 | 256)
+    NVCC_FLAGS.append("-DVS_RES_TN=" + os.environ["B200VS_RES_TN"])
+if os.environ.get("B200VS_DEBUG_BUILD") == "1":
+    NVCC_FLAGS.append("-DVS_GEMM_DEBUG_MODES")
 
 
 def _nvcc() -> str:

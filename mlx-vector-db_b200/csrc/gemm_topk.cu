@@ -55,8 +55,15 @@ constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
 constexpr int kMaxGroupTiles = 4;        // pass 1: tiles (of one CTA) per maximum
 constexpr int kGlobalCap = 4096;         // candidate slots per query over all CTAs (= K4's capacity)
 constexpr int kMaxQueriesPerLaunch = 2048;
+#ifndef VS_RES_TN
+#define VS_RES_TN 128
+#endif
+constexpr int kResTN = VS_RES_TN;        // RESIDENT: database rows per tile (MMA N), 128 or 256
 
-enum { kModeFilter = 0, kModeMax = 1, kModeDump = 2 };
+enum { kModeFilter = 0, kModeMax = 1, kModeDump = 2,
+       // diagnostic builds only (-DVS_GEMM_DEBUG_MODES, timing experiments, results are not usable):
+       kModeNop = 3,    // epilogue releases every accumulator unread: the pure TMA + MMA pipeline
+       kModeHalf = 4 }; // the filter epilogue over the first half of every accumulator's columns
 
 struct GemmParams {
   int kchunks;              // K / 64
@@ -112,6 +119,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// One lane of a converged warp, chosen by `elect.sync`.  The single-thread roles (TMA producer,
+// MMA issuer) branch on THIS rather than on `lane == 0`: with a lane-id test the compiler cannot
+// tell that exactly one thread is active and wraps every warp-uniform instruction (UTCHMMA,
+// UTCBAR, UTMALDG) in an ELECT / BRA.U.ANY serialisation loop -- measured ~110 clk per MMA for
+// the issuing thread, more than the 64 clk an M = 128, N = 128, K = 16 MMA takes to execute.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -182,7 +203,9 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, int fmt) {
 // loads and holds half; the leader (cluster rank 0) issues the MMAs for both, accumulator rows
 // land in each CTA's own TMEM.  Halves the shared-memory operand reads per MMA and the
 // database bytes each SM pulls through TMA.
-//   MMA N (database rows per tile) TN: RESIDENT CG=1: 128, otherwise 256.
+//   MMA N (database rows per tile) TN: RESIDENT 128 (four accumulators of 128 columns, so the
+//   epilogue of one overlaps the MMAs of the next three), STREAMING 256.  RESIDENT with CG = 2
+//   therefore issues M = 256, N = 128 MMAs: each CTA loads 64 database rows per tile.
 template <int CG> struct CgOps;
 template <> struct CgOps<1> {
   __device__ static __forceinline__ void alloc(uint32_t dst) {
@@ -261,7 +284,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p) {
   constexpr bool RES = MT > 0;
-  constexpr int TN = (RES && CG == 1) ? 128 : 256;        // MMA N = database rows per tile
+  constexpr bool FILT = MODE == kModeFilter || MODE == kModeHalf;
+  constexpr int TN = RES ? kResTN : 256;                  // MMA N = database rows per tile
   constexpr int TN_LOCAL = TN / CG;                       // rows of the tile this CTA loads
   constexpr int SLOTS = kTmemCols / TN;
   constexpr int B_CHUNK_BYTES = TN_LOCAL * 128;
@@ -320,7 +344,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // ================================================================ TMA producer
     // Every CTA loads its own operands; with CG = 2 the bytes of both CTAs are credited to the
     // leader's full barriers, which the leader arms with the pair's total.
-    if (lane == 0 && my_tiles > 0 && m_count > 0) {
+    if (my_tiles > 0 && m_count > 0 && elect_one()) {
       if (RES) {
         if (crank == 0) bar_expect_tx(bar_a, (uint32_t)(CG * m_count * kch * kChunkBytes));
         for (int mt = 0; mt < m_count; ++mt)
@@ -359,7 +383,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA)
-    if (lane == 0 && crank == 0 && my_tiles > 0 && m_count > 0) {
+    if (crank == 0 && my_tiles > 0 && m_count > 0 && elect_one()) {
       const uint32_t idesc = p.idesc;
       if (RES) { bar_wait(bar_a, 0); tc_fence_after(); }
       int st = 0;
@@ -431,7 +455,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     float rmax_l[MODE == kModeMax ? 16 : 1];            // pass 1: running maximum per query tile
     if (MODE == kModeMax)
       for (int mt = 0; mt < 16; ++mt) rmax_l[mt] = VS_NEG_INF;
-    if (RES && MODE == kModeFilter) {
+    if (RES && FILT) {
       for (int mt = 0; mt < NST; ++mt) {
         cnt_l[mt] = 0;
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
@@ -450,7 +474,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         float t = __int_as_float(0x7f800000);
         int c = 0;
-        if (MODE == kModeFilter) {
+        if (FILT) {
           if (RES) { t = tau_l[mt]; c = cnt_l[mt]; }
           else {
             if (q < p.nq) t = p.tau[q];
@@ -462,9 +486,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
         float rmax = MODE == kModeMax ? rmax_l[mt & 15] : VS_NEG_INF;
         float va[32], vb[32];
-        tc_ld32(taddr, va);
+        constexpr int TN_READ = MODE == kModeNop ? 0 : (MODE == kModeHalf ? TN / 2 : TN);
+        if (TN_READ > 0) tc_ld32(taddr, va);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 64) {
+        for (int c0 = 0; c0 < TN_READ; c0 += 64) {
           tc_wait_ld();
           tc_ld32(taddr + (uint32_t)(c0 + 32), vb);
 #pragma unroll
@@ -473,7 +498,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int cc = c0 + 32 * half;
             if (half == 1) {
               tc_wait_ld();
-              if (c0 + 64 < TN) tc_ld32(taddr + (uint32_t)(c0 + 64), va);
+              if (c0 + 64 < TN_READ) tc_ld32(taddr + (uint32_t)(c0 + 64), va);
             }
             if (MODE == kModeDump) {
               if (q < p.nq) {
@@ -494,7 +519,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               }
               const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
               if (MODE == kModeMax) rmax = fmaxf(rmax, m);
-              if (MODE == kModeFilter && __any_sync(0xffffffffu, m >= t)) {
+              if (FILT && __any_sync(0xffffffffu, m >= t)) {
                 // rare path (warp-uniform): re-read only the 8-column groups that hold a hit
 #pragma unroll 1
                 for (int u = 0; u < 4; ++u) {
@@ -535,7 +560,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           }
           rmax_l[mt & 15] = rmax;
         }
-        if (MODE == kModeFilter) {
+        if (FILT) {
           if (RES) cnt_l[mt] = c;
           else p.cand_cnt[(int64_t)list * q_total + q] = c;
         }
@@ -548,7 +573,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               VS_NEG_INF;
     }
     // move this thread's private candidates into the dense per-query lists
-    if (MODE == kModeFilter) {
+    if (FILT) {
       for (int mt = grp; mt < m_count; mt += kEpiGroups) {   // this warp group's query tiles
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
         if (q >= p.nq) continue;
@@ -779,13 +804,13 @@ static EncodeTiledFn encode_fn() {
 
 // (rows, K) bf16 row-major matrix, boxes of 128 rows x 64 elements, 128-byte swizzle
 // fmt: 0 = bf16, 1 = fp16, 2 = e4m3 (one byte per element, 128 elements per chunk row)
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int fmt) {
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int fmt, int box_rows = 128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VS_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const int esz = fmt == 2 ? 1 : 2;
   cuuint64_t strides[1] = {(cuuint64_t)K * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 128};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                  : (fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
@@ -809,8 +834,8 @@ struct GemmPlan {
 // bound is the TMEM read-out of the epilogue, and four 128-column accumulators per CTA (cg = 1)
 // pipeline it better than two 256-column ones.  B200VS_GEMM_CG=1|2 forces one.
 static int gemm_cta_group(int kchunks) {
-  static int forced = -1;
-  if (forced < 0) { const char* e = getenv("B200VS_GEMM_CG"); forced = e && *e ? atoi(e) : 0; }
+  const char* e = getenv("B200VS_GEMM_CG");       // read per call: tests switch it inside one process
+  const int forced = e && *e ? atoi(e) : 0;
   if (forced == 1 || forced == 2) return forced;
   return kchunks <= 4 ? 1 : 2;
 }
@@ -824,10 +849,10 @@ static void plan_gemm(int kchunks, int m_tiles, int cg, GemmPlan* plan) {
     while (mt > um_tiles) mt >>= 1;
     if (mt < 1) mt = 1;
     const size_t a = (size_t)mt * kchunks * kChunkBytes;
-    const size_t stage = (size_t)kchunks * kChunkBytes;          // 128 database rows per CTA
+    const size_t stage = (size_t)kchunks * (kResTN / cg) * 128;  // kResTN / cg database rows per CTA
     int stages = (int)((limit - a) / stage);
     if (stages > 4) stages = 4;
-    if (stages >= 2) { *plan = {mt, cg, stages, a + stages * stage + 1024 + 512, cg == 2 ? 256 : 128}; return; }
+    if (stages >= 2) { *plan = {mt, cg, stages, a + stages * stage + 1024 + 512, kResTN}; return; }
   }
   // streaming: query chunk + this CTA's share of the 256-row database chunk
   const size_t stage = (size_t)(cg == 2 ? 2 : 3) * kChunkBytes;
@@ -835,6 +860,10 @@ static void plan_gemm(int kchunks, int m_tiles, int cg, GemmPlan* plan) {
   if (stages > 6) stages = 6;
   *plan = {0, cg, stages, stages * stage + 1024 + 512, 256};
 }
+
+// rows per TMA box of the database operand: RESIDENT CTAs load 128 / cg rows per tile in one
+// box, STREAMING CTAs 256 / cg rows as one or two boxes of 128
+static int x_box_rows(const GemmPlan& plan) { return plan.mt > 0 ? std::min(128, kResTN / plan.cg) : 128; }
 
 template <int MT, int MODE, int CG>
 static int launch_gemm_tmc(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
@@ -875,6 +904,10 @@ static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const Gem
   switch (p.mode) {
     case kModeFilter: return launch_gemm_tm<MT, kModeFilter>(mq, mx, p, cg, grid, smem, stream);
     case kModeMax: return launch_gemm_tm<MT, kModeMax>(mq, mx, p, cg, grid, smem, stream);
+#ifdef VS_GEMM_DEBUG_MODES
+    case kModeNop: return launch_gemm_tm<MT, kModeNop>(mq, mx, p, cg, grid, smem, stream);
+    case kModeHalf: return launch_gemm_tm<MT, kModeHalf>(mq, mx, p, cg, grid, smem, stream);
+#endif
     default: return launch_gemm_tm<MT, kModeDump>(mq, mx, p, cg, grid, smem, stream);
   }
 }
@@ -994,6 +1027,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   // rare path is hidden and the sample only has to keep the survivors (about 1.2 kc / f per
   // query) within the candidate buffers and K4's capacity: f = kc / 1500.
   if (kch > 4) f = std::min(f, kc / 1500.0);
+  if (const char* e = getenv("B200VS_GEMM_SAMPLE")) { if (*e) f = atof(e); }   // diagnostic override
   if (f > 0.5) f = 0.5;
   if (f < 1.0 / 128) f = 1.0 / 128;
   // Maxima are taken over groups of kMaxGroupTiles tiles when there are plenty (at most 4096
@@ -1041,7 +1075,7 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   const bool fp16 = s->metric == VS_METRIC_COSINE;
   const int fmt = fp8 ? 2 : (fp16 ? 1 : 0);
   if (int rc = make_map(&mq, qb, rows_padded, K, fmt)) return rc;
-  if (int rc = make_map(&mx, fp8 ? s->shadow8_rows.ptr() : s->shadow_rows.ptr(), n, K, fmt)) return rc;
+  if (int rc = make_map(&mx, fp8 ? s->shadow8_rows.ptr() : s->shadow_rows.ptr(), n, K, fmt, x_box_rows(plan))) return rc;
 
   if (fp8)   // (the buffer is sized for 2 bytes per element; e4m3 uses half of it)
     prep_queries_fp8_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, K, rows_padded,
@@ -1069,6 +1103,11 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
     m.query_stride = s_groups; m.list_len = 0; m.k = kc; m.tau = nullptr;
     m.out_s = c1s; m.out_i = c1i; m.out_stride = kc; m.kth_out = tau;      // tau[b] = kc-th largest
     if (int rc = launch_merge(m, B, stream)) return rc;
+    // diagnostic (timing only, results are wrong): no row passes the filter, so pass 2 never
+    // takes its rare path
+    if (const char* e = getenv("B200VS_GEMM_TAU_INF")) {
+      if (*e == '1') fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, __builtin_inff(), rows_padded);
+    }
   } else {
     // tiny store: no sample, every row is a candidate of the filter (tau = -inf)
     fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, -__builtin_inff(), rows_padded);
@@ -1077,6 +1116,9 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   }
   // pass 2: threshold filter over all rows
   p.mode = kModeFilter; p.n_tiles = n_tiles; p.gmax = nullptr;
+#ifdef VS_GEMM_DEBUG_MODES
+  if (const char* e = getenv("B200VS_GEMM_DBGMODE")) { if (*e == '3' || *e == '4') p.mode = atoi(e); }
+#endif
   if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
   // K4: best kc candidates by 16-bit (or e4m3) score out of the dense per-query lists
   {
@@ -1171,7 +1213,7 @@ int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, 
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
   if (int rc = make_map(&mq, qb, rows_padded, K, fp16 ? 1 : 0)) return rc;
-  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16 ? 1 : 0)) return rc;
+  if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16 ? 1 : 0, x_box_rows(plan))) return rc;
   prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
                                                                     qerr, qlen);
   count_launch();

@@ -830,9 +830,10 @@ struct GemmPlan {
 };
 
 // CTAs per MMA.  Measured on B200: CTA pairs win where the kernel streams both
-// operands (K > 256: +9 % at D = 768, +67 % at D = 1536); with resident queries (K <= 256) the
-// bound is the TMEM read-out of the epilogue, and four 128-column accumulators per CTA (cg = 1)
-// pipeline it better than two 256-column ones.  B200VS_GEMM_CG=1|2 forces one.
+// operands (K > 256: +9 % at D = 768, +67 % at D = 1536).  With resident queries (K <= 256) one
+// CTA per MMA is faster (profiles/r01_k3_probe_experiments.txt: 2.24 vs 3.29 ms at 10 M x 128):
+// a pair's accumulator is released by eight epilogue warps in two CTAs instead of four in one.
+// B200VS_GEMM_CG=1|2 forces one.
 static int gemm_cta_group(int kchunks) {
   const char* e = getenv("B200VS_GEMM_CG");       // read per call: tests switch it inside one process
   const int forced = e && *e ? atoi(e) : 0;

@@ -45,6 +45,7 @@ def _digest() -> str:
                     [ROOT.parent / "include" / "b200vs.h", Path(__file__)]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())      # diagnostic -D knobs change the binary too
     return h.hexdigest()
 
 

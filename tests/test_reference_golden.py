@@ -3,7 +3,8 @@
 performance/mlx_optimized.py imported unmodified from /root/reference over a NumPy stand-in
 for `mlx.core`).  This is what pins the oracle: op order, clamps, slicing, id mapping, filter
 semantics, degenerate cases and exception types are the reference's; only the arithmetic inside
-the mlx primitives is NumPy's.  CPU only; nothing here reads /root/reference.
+the mlx primitives is NumPy's.  CPU only.  The committed fixtures are all these tests need; the one
+test that re-runs the generator is skipped wherever /root/reference is not mounted.
 """
 import json
 from pathlib import Path
@@ -150,3 +151,27 @@ def test_error_behaviour():
         assert want[label + "_query"] == {"raises": "RuntimeError"}
         with pytest.raises(RuntimeError):
             st.query(np.zeros(4, np.float32), k=2)
+
+
+@pytest.mark.skipif(not Path("/root/reference/service/optimized_vector_store.py").exists(),
+                    reason="the reference tree is only mounted in the build container")
+def test_fixtures_are_what_the_reference_produces_today(tmp_path):
+    """Re-run the generator against the mounted reference and compare with the committed files, so a
+    stale or hand-edited fixture cannot go unnoticed.  (CPU suite only; the GPU box has no reference.)"""
+    import shutil
+    import subprocess
+    import sys
+    work = tmp_path / "golden"
+    shutil.copytree(GOLD / "mlx_standin", work / "mlx_standin")
+    shutil.copy(GOLD / "make_reference_golden.py", work / "make_reference_golden.py")
+    subprocess.run([sys.executable, str(work / "make_reference_golden.py")], check=True, capture_output=True)
+    fresh = sorted(p.name for p in work.glob("ref_*"))
+    assert fresh == sorted(p.name for p in GOLD.glob("ref_*"))
+    for name in fresh:
+        if name.endswith(".json"):
+            assert json.loads((work / name).read_text()) == json.loads((GOLD / name).read_text()), name
+        else:
+            a, b = np.load(work / name), np.load(GOLD / name)
+            assert sorted(a.files) == sorted(b.files), name
+            for key in a.files:
+                np.testing.assert_array_equal(a[key], b[key], err_msg=f"{name}:{key}")

@@ -128,7 +128,6 @@ def fast_top_k_indices(scores, k: int) -> torch.Tensor:
     if k <= 0 or s.shape[0] == 0:
         return torch.zeros((0,), dtype=torch.int32, device=s.device)
     kk = min(int(k), s.shape[0])
-    ids = torch.arange(s.shape[0], dtype=torch.int32, device=s.device)
     out_s = torch.empty((kk,), dtype=torch.float32, device=s.device)
     out_i = torch.empty((kk,), dtype=torch.int32, device=s.device)
     _cabi.check(_topk_rows(s.reshape(1, -1), kk, out_s, out_i))

@@ -109,7 +109,7 @@ def test_store_sequences(path, make_store):
 def test_error_behaviour(native_lib):
     """Exception types and degenerate shapes equal the reference's (recorded in ref_errors.json)."""
     import torch
-    from b200vs import MLXVectorStore, MLXVectorStoreConfig, ops
+    from b200vs import ops
     want = json.loads((GOLD / "ref_errors.json").read_text())
     z4 = np.zeros((2, 4), np.float32)
     db = torch.arange(24, dtype=torch.float32).reshape(6, 4).cuda()

@@ -22,12 +22,16 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
 ]
-# tuning knob (diagnostic): B200VS_EPI_GROUPS=4 builds K3 with 16 epilogue warps
+# tuning knobs (diagnostic): epilogue warp groups of K3 (4 warps each), STREAMING / RESIDENT variants
 if os.environ.get("B200VS_EPI_GROUPS"):
     NVCC_FLAGS.append("-DVS_EPI_GROUPS=" + os.environ["B200VS_EPI_GROUPS"])
+if os.environ.get("B200VS_EPI_GROUPS_RES"):
+    NVCC_FLAGS.append("-DVS_EPI_GROUPS_RES=" + os.environ["B200VS_EPI_GROUPS_RES"])
 # diagnostic: B200VS_DEBUG_BUILD=1 adds K3's timing-experiment epilogues (B200VS_GEMM_DBGMODE)
 if os.environ.get("B200VS_RES_TN"):          # diagnostic: K3 RESIDENT tile width (128 | 256)
     NVCC_FLAGS.append("-DVS_RES_TN=" + os.environ["B200VS_RES_TN"])
+if os.environ.get("B200VS_RES_ISSUERS"):     # diagnostic: MMA-issuing warps of K3 RESIDENT (1 | 2)
+    NVCC_FLAGS.append("-DVS_RES_ISSUERS=" + os.environ["B200VS_RES_ISSUERS"])
 if os.environ.get("B200VS_DEBUG_BUILD") == "1":
     NVCC_FLAGS.append("-DVS_GEMM_DEBUG_MODES")
 

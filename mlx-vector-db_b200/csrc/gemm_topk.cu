@@ -45,8 +45,18 @@ namespace vs {
 #ifndef VS_EPI_GROUPS
 #define VS_EPI_GROUPS 2
 #endif
-constexpr int kEpiGroups = VS_EPI_GROUPS;                 // epilogue warp groups (4 warps each)
-constexpr int kGemmThreads = 128 + 128 * kEpiGroups;      // 4 control warps + the epilogue warps
+#ifndef VS_EPI_GROUPS_RES
+#define VS_EPI_GROUPS_RES 2
+#endif
+// epilogue warp groups (4 warps each; query tile mt belongs to group mt % groups), separately
+// for the STREAMING (K > 256) and RESIDENT (K <= 256) variants.  Measured at 10 M x 128, batch
+// 1024 (profiles/r01_k3_probe_experiments.txt): four groups are 5 % SLOWER than two for RESIDENT,
+// with one MMA-issuing warp (2.37 vs 2.24-2.33 ms) and with two (2.21 vs 2.10 ms).
+constexpr int kEpiGroupsStream = VS_EPI_GROUPS;
+constexpr int kEpiGroupsRes = VS_EPI_GROUPS_RES;
+__host__ __device__ constexpr int epi_groups(bool resident) { return resident ? kEpiGroupsRes : kEpiGroupsStream; }
+// 4 control warps + the epilogue warps
+__host__ __device__ constexpr int gemm_threads(bool resident) { return 128 + 128 * epi_groups(resident); }
 constexpr int kTileM = 128;              // queries per m-tile = TMEM lanes
 constexpr int kChunkK = 64;              // bf16 elements per 128-byte swizzled row
 constexpr int kChunkBytes = 128 * 128;   // 128 rows x 128 B
@@ -55,6 +65,10 @@ constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
 constexpr int kMaxGroupTiles = 4;        // pass 1: tiles (of one CTA) per maximum
 constexpr int kGlobalCap = 4096;         // candidate slots per query over all CTAs (= K4's capacity)
 constexpr int kMaxQueriesPerLaunch = 2048;
+#ifndef VS_RES_ISSUERS
+#define VS_RES_ISSUERS 2
+#endif
+constexpr int kResIssuers = VS_RES_ISSUERS;   // RESIDENT: warps that issue MMAs (1: warp 1; 2: warps 1 and 3)
 #ifndef VS_RES_TN
 #define VS_RES_TN 128
 #endif
@@ -280,10 +294,11 @@ __device__ __forceinline__ void bar_arrive_remote(uint32_t bar, uint32_t rank) {
 }
 
 template <int MT, int MODE, int CG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(MT > 0), 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p) {
   constexpr bool RES = MT > 0;
+  constexpr int kEpiGroups = epi_groups(RES);
   constexpr bool FILT = MODE == kModeFilter || MODE == kModeHalf;
   constexpr int TN = RES ? kResTN : 256;                  // MMA N = database rows per tile
   constexpr int TN_LOCAL = TN / CG;                       // rows of the tile this CTA loads
@@ -329,7 +344,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   if (threadIdx.x == 0) {
     bar_init(bar_a, 1);
-    for (int i = 0; i < p.stages; ++i) { bar_init(bar_full + 8 * i, 1); bar_init(bar_empty + 8 * i, 1); }
+    // a RESIDENT stage is released by every MMA-issuing warp (one tcgen05.commit each)
+    for (int i = 0; i < p.stages; ++i) { bar_init(bar_full + 8 * i, 1); bar_init(bar_empty + 8 * i, RES ? kResIssuers : 1); }
     for (int i = 0; i < SLOTS; ++i) { bar_init(bar_accf + 8 * i, 1); bar_init(bar_acce + 8 * i, 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -381,8 +397,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (RES && kResIssuers == 2 && warp == 3)) {
     // ================================================================ MMA issuer (leader CTA)
+    // RESIDENT at K <= 256 is bound by how fast ONE thread can issue: ~117 SASS instructions per
+    // accumulator (barrier wait, two descriptors per K chunk, 8 MMAs, commit) on a single warp's
+    // dependent uniform-datapath chain take 700-800 clk, the 8 MMAs execute in 512 (ncu: the
+    // issuing warp 85 % busy, tensor pipe 63 %).  So two warps issue, taking alternate accumulators
+    // (`it` parity: with 4 query tiles each warp always owns the same two TMEM slots); MMAs of
+    // different accumulators are independent, both warps read the same shared-memory operands and
+    // each releases the stage with its own commit.
+    const int issuer = warp == 1 ? 0 : 1;
     if (crank == 0 && my_tiles > 0 && m_count > 0 && elect_one()) {
       const uint32_t idesc = p.idesc;
       if (RES) { bar_wait(bar_a, 0); tc_fence_after(); }
@@ -395,6 +419,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           tc_fence_after();
         }
         for (int mt = 0; mt < m_count; ++mt, ++it) {
+          if (RES && kResIssuers == 2 && (it & 1) != issuer) continue;   // the other issuing warp's
           const int slot = it % SLOTS;
           const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
           bar_wait(bar_acce + 8 * slot, aph ^ 1u);      // epilogues drained this accumulator
@@ -873,7 +898,7 @@ static int launch_gemm_tmc(const CUtensorMap& mq, const CUtensorMap& mx, const G
   VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(gemm_threads(MT > 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -32,6 +32,8 @@ if os.environ.get("B200VS_RES_TN"):          # diagnostic: K3 RESIDENT tile widt
     NVCC_FLAGS.append("-DVS_RES_TN=" + os.environ["B200VS_RES_TN"])
 if os.environ.get("B200VS_RES_ISSUERS"):     # diagnostic: MMA-issuing warps of K3 RESIDENT (1 | 2)
     NVCC_FLAGS.append("-DVS_RES_ISSUERS=" + os.environ["B200VS_RES_ISSUERS"])
+if os.environ.get("B200VS_RARE_REGS"):       # experimental: register-based rare path of K3's filter epilogue
+    NVCC_FLAGS.append("-DVS_RARE_REGS=" + os.environ["B200VS_RARE_REGS"])
 if os.environ.get("B200VS_DEBUG_BUILD") == "1":
     NVCC_FLAGS.append("-DVS_GEMM_DEBUG_MODES")
 

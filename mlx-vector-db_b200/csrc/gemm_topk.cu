@@ -65,6 +65,9 @@ constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
 constexpr int kMaxGroupTiles = 4;        // pass 1: tiles (of one CTA) per maximum
 constexpr int kGlobalCap = 4096;         // candidate slots per query over all CTAs (= K4's capacity)
 constexpr int kMaxQueriesPerLaunch = 2048;
+#ifndef VS_RARE_REGS
+#define VS_RARE_REGS 0                   // 1: experimental register-based rare path of the filter epilogue
+#endif
 #ifndef VS_RES_ISSUERS
 #define VS_RES_ISSUERS 2
 #endif
@@ -545,6 +548,36 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
               if (MODE == kModeMax) rmax = fmaxf(rmax, m);
               if (FILT && __any_sync(0xffffffffu, m >= t)) {
+#if VS_RARE_REGS
+                // rare path, EXPERIMENTAL (off by default, not yet run on a B200): take the hits
+                // straight from the registers of this chunk instead of re-reading TMEM.  Per
+                // 8-column group one warp-uniform vote; inside, a branch-free hit mask per lane
+                // and a (divergent, almost always single-trip) loop over its set bits that picks
+                // the value with a select chain -- no per-value branches, no tcgen05.ld round trip.
+                const int lim = (int)min((int64_t)TN, p.n_rows - (int64_t)nt * TN) - cc;   // live columns
+                const int32_t id0 = (int32_t)((int64_t)nt * TN + cc);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (!__any_sync(0xffffffffu, g[u] >= t)) continue;
+                  uint32_t hits = 0;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) hits |= (v[8 * u + j] >= t ? 1u : 0u) << j;
+                  const int live = lim - 8 * u;                       // columns of this group inside the store
+                  hits &= live >= 8 ? 0xffu : (live <= 0 ? 0u : (1u << live) - 1u);
+                  while (hits) {
+                    const int j = __ffs((int)hits) - 1;
+                    hits &= hits - 1u;
+                    float w = v[8 * u];
+#pragma unroll
+                    for (int jj = 1; jj < 8; ++jj) w = j == jj ? v[8 * u + jj] : w;
+                    if (c < kCandCap) {
+                      p.cand_score[cbase + c] = w;
+                      p.cand_id[cbase + c] = id0 + 8 * u + j;
+                    }
+                    ++c;
+                  }
+                }
+#else
                 // rare path (warp-uniform): re-read only the 8-column groups that hold a hit
 #pragma unroll 1
                 for (int u = 0; u < 4; ++u) {
@@ -566,6 +599,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                   }
                 }
                 // the reload waited for every outstanding tcgen05.ld, including the prefetch
+#endif
               }
             }
           }

@@ -17,7 +17,6 @@ uncertified queries fall back to the exact scan.
 import numpy as np
 import pytest
 
-F16_EPS = 2.0 ** -11
 SAFETY = np.float32(1.00001)          # the kernels inflate every norm they store by this factor
 
 

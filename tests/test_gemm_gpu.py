@@ -85,6 +85,7 @@ SEARCH_SHAPES = [
     (70000, 128, 64, 10),
     (100000, 128, 256, 10),
     (80000, 128, 1024, 10),
+    (70000, 128, 800, 10),     # 7 query tiles: one CTA group holds 4, the other 3 (odd count per MMA-issuing warp)
     (66000, 96, 130, 5),
     (70001, 256, 200, 10),
     (66000, 384, 128, 10),     # streaming kernel

@@ -188,7 +188,8 @@ class MLXVectorStore:
 
     def _search_host(self, q: np.ndarray, k: int, filter_metadata: Optional[Dict]):
         B = q.shape[0]
-        if k <= 0:
+        k = int(k)
+        if k == 0:
             return [([], [], []) for _ in range(B)]
         row_mask = None
         n_live = self._vector_count
@@ -208,7 +209,11 @@ class MLXVectorStore:
                 bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
             row_mask = torch.from_numpy(bits.view(np.int32).copy()).to(f"cuda:{self.config.device}")
             torch.cuda.current_stream(row_mask.device).synchronize()
-        kk = min(int(k), n_live)
+        # the reference slices `argsort(...)[:k]` (:178,:181): k > N returns N results, a negative k
+        # drops the last |k| of the (filtered) rows
+        kk = min(k, n_live) if k > 0 else max(0, n_live + k)
+        if kk == 0:
+            return [([], [], []) for _ in range(B)]
         ids, scores = self.search_arrays(q, kk, row_mask=row_mask)
         out = []
         for b in range(B):

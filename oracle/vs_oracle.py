@@ -281,10 +281,11 @@ class OracleVectorStore:
         if target.shape[0] == 0:
             return [], [], []
         s = self._fn(q, target)
+        # `[:k]` is a Python slice in the reference (:178,:181): k = 0 -> empty, k < 0 drops the last |k|
         if self.metric == "euclidean":
-            order = np.argsort(s, kind="stable")[:max(k, 0)]
+            order = np.argsort(s, kind="stable")[:k]
         else:
-            order = np.argsort(-s, kind="stable")[:max(k, 0)]
+            order = np.argsort(-s, kind="stable")[:k]
         top = s[order]
         idx = [original[i] for i in order.tolist()] if original is not None else order.tolist()
         return idx, top.tolist(), [self._metadata[i] for i in idx]

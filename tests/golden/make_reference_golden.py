@@ -108,7 +108,8 @@ def store_case(name, db, q, k, metric, batches):
         filters = [None, {"group": 2}, {"group": 3, "parity": "odd"}, {"group": 99}]
         for qi, row in enumerate(q):
             for f in filters:
-                for kk in (k, db.shape[0] + 5) if (qi == 0 and f is None) else (k,):
+                # k > N, k = 0 and a negative k (the reference slices `argsort(...)[:k]`, so -3 drops the last 3)
+                for kk in (k, db.shape[0] + 5, 0, -3) if (qi == 0 and f in (None, {"group": 2})) else (k,):
                     ids, scores, metas = st.query(row, k=kk, filter_metadata=f)
                     record["queries"].append({"q": qi, "k": kk, "filter": f, "ids": [int(i) for i in ids],
                                               "scores": [float(np.float32(s)) for s in scores],

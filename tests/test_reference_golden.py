@@ -103,7 +103,11 @@ def test_behavioural_pins_hold_in_the_reference_fixtures():
     first = rec["queries"][0]                     # query = stored row 3 (duplicated at 20, 21)
     assert first["ids"][:3] == [3, 20, 21] and first["scores"][0] > 0.999      # self-match, ties -> lower id
     for item in rec["queries"]:
-        assert len(item["ids"]) <= item["k"]
+        n_match = 130 if not item["filter"] else sum(
+            all((i % 5 if key == "group" else ("even" if i % 2 == 0 else "odd")) == val
+                for key, val in item["filter"].items()) for i in range(130))
+        # `argsort(...)[:k]` is a Python slice: k > N -> N results, k = 0 -> none, k < 0 drops the last |k|
+        assert len(item["ids"]) == (min(item["k"], n_match) if item["k"] >= 0 else max(0, n_match + item["k"]))
         if item["filter"] == {"group": 99}:
             assert item["ids"] == []               # no match -> empty, not an error
         elif item["filter"]:

@@ -20,7 +20,8 @@
 //
 // Kernel anatomy (one CTA per SM, 384 threads): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane; RESIDENT: warps 1 and 3 issue alternate accumulators), warp 2 = TMEM
-// allocator, warps 4-11 = epilogue (two groups of four, TMEM lane quadrant = warp % 4).  Operands are bf16, K-major, 128-byte swizzled: one "chunk" is 128 rows x 64
+// allocator, warps 4-11 = epilogue (two groups of four, TMEM lane quadrant = warp % 4).
+// Operands are 16-bit, K-major, 128-byte swizzled: one "chunk" is 128 rows x 64
 // elements = 16 KB, loaded by one cp.async.bulk.tensor.2d.
 //   RESIDENT (K <= 256): the CTA's query tiles (up to 4 x 128 queries) are loaded once and stay
 //     in shared memory; database tiles of 128 rows stream through a ring; 4 TMEM accumulators

@@ -188,13 +188,30 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def reference_step(db_np, q_np, k, sample_q, threads):
+def set_host_threads(threads: int):
+    """torchrun exports OMP_NUM_THREADS=1 for nproc > 1, which would leave the BLAS of the CPU arm
+    single-threaded at N >= 2: pin every native thread pool to the cores this process may use."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=threads)
+    except Exception:
+        return None
+
+
+def cpu_sample_queries(threads: int, B: int) -> int:
+    """Queries per CPU sample: one per host thread (the per-row argsort runs one row per thread, so
+    fewer would leave cores idle and bias the extrapolation), the same at every N."""
+    return max(1, min(B, threads))
+
+
+def reference_step(db_np, q_np, k, sample_q, threads, return_scores=False):
     """One bounded sample of the reference's batch search on the host: the first `sample_q`
     queries of the batch against the FULL database, in the reference's op order (per-call
-    database re-normalisation, fp32 GEMM, full stable argsort).  Returns (phase times, ids)."""
+    database re-normalisation, fp32 GEMM, full stable argsort).  Returns (phase times, ids, scores)."""
     from oracle import vs_oracle
-    ids, _, t = vs_oracle.batch_similarity_search_timed(q_np[:sample_q], db_np, k, threads=threads)
-    return t, ids
+    ids, sc, t = vs_oracle.batch_similarity_search_timed(q_np[:sample_q], db_np, k, threads=threads,
+                                                        return_scores=return_scores)
+    return t, ids, sc
 
 
 def extrapolate_qps(t: dict, sample_q: int, B: int) -> float:
@@ -202,6 +219,32 @@ def extrapolate_qps(t: dict, sample_q: int, B: int) -> float:
     call, GEMM and argsort scale with the number of queries."""
     per_q = (t["matmul_s"] + t["argsort_s"]) / sample_q
     return B / (t["normalize_s"] + B * per_q)
+
+
+def optimized_cpu_line(db_np, q_np, k, sample_q, threads, B):
+    """BASELINE.md section 2's "optimised CPU" line: database normalised once (untimed), GEMM,
+    argpartition to k + sort of k.  Context for how much of the reference's cost is algorithmic."""
+    from oracle import vs_oracle
+    vn = vs_oracle.normalize_vectors(db_np)
+    vs_oracle.batch_similarity_search_optimized_timed(q_np[:sample_q], vn, k, threads)      # warm-up
+    _, _, t = vs_oracle.batch_similarity_search_optimized_timed(q_np[:sample_q], vn, k, threads)
+    per_q = (t["matmul_s"] + t["select_s"]) / sample_q
+    return {"value": 1.0 / per_q, "unit": "queries/s", "cores": threads,
+            "what": "pre-normalised database (once, untimed) + fp32 GEMM + argpartition(k) + sort of k",
+            "sample": f"first {sample_q} of {B} queries vs the full database; GEMM {t['matmul_s']:.2f}s, "
+                      f"select {t['select_s']:.2f}s"}
+
+
+def verify_against_oracle(ref_ids, ref_scores, score_matrix, got_ids, got_scores):
+    """--verify: the engine's results for the sampled queries against the oracle's, BASELINE.json's
+    contract (ids exact outside 1e-6 ties, scores within 1e-5) -- oracle/compare.py."""
+    from oracle import compare
+    q = ref_ids.shape[0]
+    rep = compare.compare_topk(ref_ids, ref_scores, got_ids[:q], got_scores[:q], score_matrix)
+    return {"queries": int(q), "ok": bool(rep.ok), "ids_exact": int(rep.id_exact), "ids_tie_ok": int(rep.id_tie_ok),
+            "ids_wrong": int(rep.id_wrong), "max_score_err": float(rep.max_score_err),
+            "against": "NumPy oracle (reference op order) over the FULL database, tie rule of oracle/compare.py",
+            "first_failure": rep.first_failure}
 
 
 def make_host_data(n, d, B):
@@ -224,81 +267,109 @@ def run_reference(args):
     n, d = WORKLOADS[args.workload]
     B, k = args.batch, args.k
     threads = host_cores()
+    limiter = set_host_threads(threads)
     db, q = make_host_data(n, d, B)
-    # size the per-step sample so warmup+steps end within a few minutes
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
-    t, _ = reference_step(db, q, k, 1, threads)
-    per_q = t["matmul_s"] + t["argsort_s"]
-    sample_q = int(max(1, min(B, (budget_s - t["normalize_s"]) / max(per_q, 1e-9))))
-    sample_q = min(sample_q, 4 * threads)
-    for _ in range(max(0, args.warmup - 1)):
+    sample_q = cpu_sample_queries(threads, B)
+    # bound the run: warmup + steps samples within ~3 minutes
+    t, _, _ = reference_step(db, q, k, sample_q, threads)
+    one = t["normalize_s"] + t["matmul_s"] + t["argsort_s"]
+    steps = max(1, min(args.steps, int(170.0 / max(one, 1e-3)) - 1))
+    warm = max(0, min(args.warmup - 1, int(170.0 / max(one, 1e-3)) - 1 - steps))
+    for _ in range(warm):
         reference_step(db, q, k, sample_q, threads)
     vals, wall = [], 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        t, _ = reference_step(db, q, k, sample_q, threads)
+        t, _, _ = reference_step(db, q, k, sample_q, threads)
         wall += time.perf_counter() - t0
         vals.append(extrapolate_qps(t, sample_q, B))
     value = len(vals) / sum(1.0 / v for v in vals)
-    sample = (f"per step: first {sample_q} of {B} queries vs the full {n}x{d} database "
+    sample = (f"per step: first {sample_q} of {B} queries (one per host thread) vs the full {n}x{d} database "
               f"(normalise DB + fp32 GEMM + full stable argsort); QPS extrapolated to the batch as "
-              f"B/(t_normalise + B*(t_gemm+t_argsort)/{sample_q})")
+              f"B/(t_normalise + B*(t_gemm+t_argsort)/{sample_q}); {steps} timed samples")
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+        "ms_per_step": 1e3 * wall / max(1, steps), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload} fp32 cosine top-{k}, batch {B}", "rows": n, "dim": d,
-                   "batch": B, "k": k, "sample_queries_per_step": sample_q},
+                   "batch": B, "k": k, "sample_queries_per_step": sample_q, "timed_samples": steps},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    del limiter
 
 
 # --------------------------------------------------------------------------- extra configs (N = 1)
 def config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args):
-    """BASELINE config C: 1M x 1536 L2 top-100, bf16 database scan + fp32 rescoring of the
-    candidates; recall@100 against the engine's own exact fp32 scan (itself oracle-checked in
-    tests/) and throughput at batch 1 and 16."""
+    """BASELINE config C: 1M x 1536 L2 top-100 over the bf16 shadow of the database with fp32
+    rescoring of the candidates.  recall@100 is against the ORACLE's ids (direct-difference
+    euclidean distance + stable argsort over a host copy of the same rows, first 8 queries);
+    throughput for the tensor-core path (K3, certified: batches) and the scans (batch 1)."""
+    import numpy as np
     import torch
+    from oracle import vs_oracle
     n, d, k = 1_000_000, 1536, 100
     out = {"workload": "1Mx1536 L2 top-100, bf16 database + fp32 rescoring (config C)"}
-    exact = ShardedVectorStore(d, "euclidean", device=dev, shadow_bf16=True, max_vectors_per_shard=n + 16,
-                               search_mode="scan_fp32")
+    st = ShardedVectorStore(d, "euclidean", device=dev, shadow_bf16=True, max_vectors_per_shard=n + 16,
+                            search_mode="auto")
+    host_blocks = []
     for b in range(N_BLOCKS):
         g = torch.Generator(device=dev).manual_seed(DB_SEED + b)
         rows = torch.randn((n // N_BLOCKS, d), generator=g, device=dev, dtype=torch.float32)
-        exact.shard.append(rows, b * (n // N_BLOCKS))
+        st.shard.append(rows, b * (n // N_BLOCKS))
+        host_blocks.append(rows.cpu().numpy())
         del rows
-    exact.total = n
-    q = torch.randn((16, d), generator=torch.Generator().manual_seed(QUERY_SEED), dtype=torch.float32).to(dev)
-    ref_ids, _ = exact.search(q, k)
-    exact.shard.flags = _cabi.SEARCH_MODES["scan_bf16"]        # same store, 16-bit scan + K5
-    got_ids, _ = exact.search(q, k)
-    ref = ref_ids.cpu().numpy()
-    got = got_ids.cpu().numpy()
-    hits = sum(len(set(r.tolist()) & set(g_.tolist())) for r, g_ in zip(ref, got))
-    out["recall_at_100_vs_exact_fp32"] = hits / ref.size
-    for B in (1, 16):
+    st.total = n
+    q = torch.randn((1024, d), generator=torch.Generator().manual_seed(QUERY_SEED), dtype=torch.float32).to(dev)
+    nq = 8
+    q_np = q[:nq].cpu().numpy()
+    dist_rows = np.concatenate([np.stack([vs_oracle.euclidean_distance(qi, blk) for qi in q_np]) for blk in host_blocks],
+                               axis=1)                                   # (nq, n) oracle distances
+    del host_blocks
+    ref = np.argsort(dist_rows, axis=1, kind="stable")[:, :k]
+
+    def recall(ids):
+        got = ids[:nq].cpu().numpy()
+        return sum(len(set(r.tolist()) & set(g_.tolist())) for r, g_ in zip(ref, got)) / ref.size
+
+    def timed(B, mode, steps=10):
+        st.shard.flags = _cabi.SEARCH_MODES[mode]
         qq = q[:B].contiguous()
+        fb0 = int(lib.vs_fallback_count(st.shard.handle))
         for _ in range(3):
-            exact.search(qq, k)
+            ids, _ = st.search(qq, k)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        steps = 20
         e0.record()
-        for _ in range(steps):
-            exact.search(qq, k)
+        pend = st.submit(qq, k)
+        for _ in range(steps - 1):
+            nxt = st.submit(qq, k)
+            st.result(pend)
+            pend = nxt
+        ids, _ = st.result(pend)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        out[f"batch{B}_qps"] = B / (ms * 1e-3)
-        out[f"batch{B}_ms_per_step"] = ms
-        out[f"batch{B}_scan_gbs_of_bf16_bytes"] = n * d * 2 / (ms * 1e-3) / 1e9
-    exact.close()
+        r = {"mode": mode, "batch": B, "qps": B / (ms * 1e-3), "ms_per_step": ms,
+             "exact_fallback_queries_per_step": (int(lib.vs_fallback_count(st.shard.handle)) - fb0) / (steps + 3)}
+        if B >= nq:
+            r["recall_at_100_vs_oracle"] = recall(ids)
+        if B == 1:
+            bytes_per_row = d * (4 if mode == "scan_fp32" else 2)
+            r["hbm_gbs_of_scanned_rows"] = n * bytes_per_row / (ms * 1e-3) / 1e9
+        else:
+            r["tflops"] = 2.0 * B * n * d / (ms * 1e-3) / 1e12
+        return r
+
+    out["runs"] = [timed(1024, "auto"), timed(16, "auto"), timed(8, "scan_bf16", 5),
+                   timed(1, "scan_bf16", 20), timed(1, "gemm", 20), timed(1, "scan_fp32", 20)]
+    out["note"] = ("auto = K3 (tcgen05 over the bf16 shadow, key 2 q.x - ||x||^2, certified, exact fp32 results) for "
+                   "batches, the fp32 scan for single queries; scan_bf16 = K2 over the bf16 shadow + K5 (recall-reported)")
+    st.close()
     torch.cuda.empty_cache()
     return out
 
@@ -514,9 +585,16 @@ def run_b200(args):
         sampler = make_sampler(args.clocks, local_rank)
         if rank == 0:
             sampler.start()
+        # every step submits one batch and collects one: two searches are in flight, so a batch's
+        # certification count reaches the host (and its candidates cross NVLink at N > 1) while
+        # the next batch already runs -- ShardedVectorStore.submit / result
         e0.record()
-        for _ in range(steps):
-            ids, scores = st.search(q_dev, k)
+        pend = st.submit(q_dev, k)
+        for _ in range(steps - 1):
+            nxt = st.submit(q_dev, k)
+            ids, scores = st.result(pend)
+            pend = nxt
+        ids, scores = st.result(pend)
         e1.record()
         barrier()
         clocks = sampler.stop() if rank == 0 else {}
@@ -531,8 +609,12 @@ def run_b200(args):
             if rank == 0:
                 sampler.start()
                 time.sleep(0.05)
-            for _ in range(extra):
-                st.search(q_dev, k)
+            pend = st.submit(q_dev, k)
+            for _ in range(extra - 1):
+                nxt = st.submit(q_dev, k)
+                st.result(pend)
+                pend = nxt
+            st.result(pend)
             barrier()
             if rank == 0:
                 clocks = sampler.stop()
@@ -548,22 +630,41 @@ def run_b200(args):
         n_local = n // world
         if gemm_n and gemm_ms >= scan_ms:
             # K3 runs twice per step (sample pass + full pass): the algorithmic work of a step is
-            # 2*B*N_local*D flops, set against the summed duration of the step's GEMM launches
+            # 2*B*N_local*D flops and one pass over the N_local*D 16-bit rows, set against the summed
+            # duration of the step's GEMM launches; the slower of the two rooflines bounds it
             flops = 2.0 * B * n_local * d
+            bytes16 = float(n_local) * d * 2
             per_step = gemm_ms / steps
-            ach = flops / (per_step * 1e-3) / 1e12
             peak = tc_sust if ms > 1000 else tc_burst
-            res["roofline"] = {"kernel": "gemm_topk (K3, tcgen05 bf16)", "bound": "tensor", "achieved": ach,
-                               "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                               "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16 cuBLAS "
-                                              f"({'sustained' if ms > 1000 else 'burst'})",
-                               "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
-                               "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
-                               "scan_fallback_ms_per_step": scan_ms / steps,
-                               # the runs are power-capped (clocks.reasons): the sustained cuBLAS figure
-                               "frac_of_sustained_peak": ach / tc_sust, "sustained_peak": tc_sust,
-                               # small batches are HBM-bound on the 16-bit shadow copy they stream
-                               "hbm_gbs_of_16bit_rows": float(n_local) * d * 2 / (per_step * 1e-3) / 1e9}
+            kname = ("gemm_topk (K3: tcgen05 kind::f16, fp16 operands for cosine / bf16 for dot and "
+                     "euclidean, fp32 accumulators in TMEM; pass 1 sample + pass 2 filter)")
+            if flops / (peak * 1e12) >= bytes16 / (hbm_peak * 1e9):
+                ach = flops / (per_step * 1e-3) / 1e12
+                res["roofline"] = {"kernel": kname, "bound": "tensor", "achieved": ach,
+                                   "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                                   "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16 cuBLAS "
+                                                  f"({'sustained' if ms > 1000 else 'burst'})",
+                                   "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
+                                   "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
+                                   "scan_fallback_ms_per_step": scan_ms / steps,
+                                   # the runs are power-capped (clocks.reasons): the sustained cuBLAS figure
+                                   "frac_of_sustained_peak": ach / tc_sust, "sustained_peak": tc_sust,
+                                   "hbm_gbs_of_16bit_rows": bytes16 / (per_step * 1e-3) / 1e9}
+            else:
+                # small batches: K3 is HBM-bound on the 16-bit rows it streams (half the bytes of the
+                # fp32 rows the exact scan reads, with the same exact results by certification)
+                ach = bytes16 / (per_step * 1e-3) / 1e9
+                res["roofline"] = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                                   "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                                   "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
+                                   "algorithmic_bytes": "N_local * D * 2 (one pass over the 16-bit shadow rows)",
+                                   "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
+                                   "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
+                                   "scan_fallback_ms_per_step": scan_ms / steps,
+                                   # north_star's roofline for the fp32 path: fp32 database bytes / HBM peak
+                                   "fp32_scan_roofline_qps": B / (float(n_local) * d * 4 / (hbm_peak * 1e9)),
+                                   "qps_vs_fp32_scan_roofline": (B * steps / (ms / 1e3)) /
+                                                                (B / (float(n_local) * d * 4 / (hbm_peak * 1e9)))}
         elif scan_n:
             per = scan_ms / scan_n
             bytes_per_launch = float(n_local) * d * 4   # one pass over the fp32 rows of this shard
@@ -574,14 +675,14 @@ def run_b200(args):
                                "launches": int(scan_n), "avg_launch_ms": per,
                                "kernel_share_of_step": scan_ms / ms}
         if world == 1 and "roofline" in res:
-            tp = ROOT / "profiles" / "traffic_r01.json"
+            tp = ROOT / "profiles" / "traffic_r02.json"
             if tp.exists():
                 kind = "gemm" if res["roofline"]["bound"] == "tensor" else "scan"
                 ent = json.loads(tp.read_text()).get(f"{wl_name}|{B}|{kind}")
                 if ent:
                     res["roofline"]["traffic"] = ent["bytes"]
                     res["roofline"]["traffic_note"] = ("DRAM bytes per step from the committed ncu capture "
-                                                       "(profiles/traffic_r01.json): " + ent["note"])
+                                                       "(profiles/traffic_r02.json): " + ent["note"])
         # ---- end to end: host buffers in, host buffers out, every step ----
         if with_e2e:
             out_s = torch.empty((B, k), dtype=torch.float32).pin_memory()
@@ -592,7 +693,7 @@ def run_b200(args):
                 if world == 1:
                     # the C-ABI call MLXVectorStore.query()/batch_query() make (host pointers)
                     _cabi.check(lib.vs_search_host(st.shard.handle, C.c_void_p(q_host.data_ptr()), B, k,
-                                                   flags, None, C.c_void_p(out_s.data_ptr()),
+                                                   flags, None, -1, C.c_void_p(out_s.data_ptr()),
                                                    C.c_void_p(out_i.data_ptr())))
                 else:
                     qd = q_host.to(dev, non_blocking=True)
@@ -625,22 +726,25 @@ def run_b200(args):
     assert (np.diff(sc_h, axis=1) <= 0).all(), "scores not sorted"
     checksum = int(np.bitwise_xor.reduce(ids_h.astype(np.int64).ravel() * 2654435761 % (1 << 31)))
 
+    def entry(name, r):
+        return {"workload": name, "qps": r["qps"], "ms_per_step": r["ms_per_step"], "roofline": r.get("roofline"),
+                "e2e_qps": r["e2e"]["value"] if "e2e" in r else None,
+                "exact_fallback_queries_per_step": r["exact_fallback_queries_per_step"],
+                "wide_retry_queries_per_step": r["wide_retry_queries_per_step"]}
+
     extras = []
     do_extras = args.extras if args.extras >= 0 else (1 if world == 1 else 0)
+    # batch 1 on the same sharded store at every N (north_star's 8-GPU target covers batch 1 too)
+    r = measure(st, n, d, 1, k, max(50, args.steps), args.warmup, wl_name=args.workload)
+    extras.append(entry(f"{args.workload} batch 1 (AUTO: 16-bit tensor-core prefilter + certified fp32 rescoring)", r))
     if do_extras:
         short = max(3, min(args.steps, 10))
+        st.shard.flags = _cabi.SEARCH_MODES["scan_fp32"]
         r = measure(st, n, d, 1, k, max(20, args.steps), args.warmup, wl_name=args.workload)
-        extras.append({"workload": f"{args.workload} batch 1", "qps": r["qps"], "ms_per_step": r["ms_per_step"],
-                       "roofline": r.get("roofline"), "e2e_qps": r["e2e"]["value"]})
+        extras.append(entry(f"{args.workload} batch 1 via the fp32 scan (K2, mode scan_fp32)", r))
+        st.shard.flags = _cabi.SEARCH_MODES[args.mode]
         r = measure(st, n, d, 32, k, max(20, args.steps), args.warmup)
-        extras.append({"workload": f"{args.workload} batch 32", "qps": r["qps"], "ms_per_step": r["ms_per_step"],
-                       "roofline": r.get("roofline"), "e2e_qps": r["e2e"]["value"]})
-        st.shard.flags = _cabi.SEARCH_MODES["gemm"]
-        r = measure(st, n, d, 1, k, max(20, args.steps), args.warmup)
-        extras.append({"workload": f"{args.workload} batch 1 via the 16-bit GEMM prefilter + certified fp32 rescoring "
-                                   f"(mode gemm; AUTO keeps the fp32 scan for single queries)",
-                       "qps": r["qps"], "ms_per_step": r["ms_per_step"], "roofline": r.get("roofline"),
-                       "e2e_qps": r["e2e"]["value"]})
+        extras.append(entry(f"{args.workload} batch 32", r))
         st.close()
         del st
         torch.cuda.empty_cache()
@@ -649,9 +753,11 @@ def run_b200(args):
             st2 = build_store(n2, d2, args.mode)
             for b2 in batches:
                 r = measure(st2, n2, d2, b2, k, max(20, args.steps) if b2 == 1 else short, args.warmup, wl_name=name)
-                extras.append({"workload": f"{name} batch {b2}", "qps": r["qps"],
-                               "ms_per_step": r["ms_per_step"], "roofline": r.get("roofline"),
-                               "e2e_qps": r["e2e"]["value"]})
+                extras.append(entry(f"{name} batch {b2}", r))
+            if name == "1Mx1536":
+                st2.shard.flags = _cabi.SEARCH_MODES["scan_fp32"]
+                r = measure(st2, n2, d2, 1, k, max(20, args.steps), args.warmup, wl_name=name)
+                extras.append(entry(f"{name} batch 1 via the fp32 scan (K2, mode scan_fp32)", r))
             st2.close()
             del st2
             torch.cuda.empty_cache()
@@ -662,23 +768,32 @@ def run_b200(args):
     else:
         st.close()
 
+    # ---- CPU leg (rank 0): the oracle over the FULL database for one query per host thread.  Its ids
+    # verify the engine's (--verify, any N); its timing is the cpu_baseline (N = 1 only).
     cpu_baseline = None
-    if rank == 0 and world == 1 and args.cpu_baseline:
+    verified = None
+    if rank == 0 and (args.verify or (world == 1 and args.cpu_baseline)):
         threads = host_cores()
+        limiter = set_host_threads(threads)
         db_np, q_np = make_host_data(n, d, B)
-        t, _ = reference_step(db_np, q_np, k, 1, threads)
-        per_q = t["matmul_s"] + t["argsort_s"]
-        sample_q = int(max(1, min(B, 4 * threads, (20.0 - t["normalize_s"]) / max(per_q, 1e-9))))
-        t, _ = reference_step(db_np, q_np, k, sample_q, threads)
-        cpu_baseline = {
-            "value": extrapolate_qps(t, sample_q, B), "unit": "queries/s", "cores": threads, "kind": "port",
-            "sample": (f"first {sample_q} of {B} queries vs the full {n}x{d} database on the host, reference op "
-                       f"order (per-call DB re-normalisation {t['normalize_s']:.2f}s, fp32 GEMM "
-                       f"{t['matmul_s']:.2f}s, full stable argsort {t['argsort_s']:.2f}s); QPS extrapolated to "
-                       f"the batch as B/(t_norm + B*(t_gemm+t_sort)/{sample_q}); NumPy port of the reference "
-                       f"(mlx not installable)"),
-        }
-        del db_np
+        sample_q = cpu_sample_queries(threads, B)
+        if args.dist != "normal":
+            args.verify = 0            # the host copy is generated for N(0,1) data only
+        t, ref_ids, ref_sc = reference_step(db_np, q_np, k, sample_q, threads, return_scores=bool(args.verify))
+        if args.verify:
+            verified = verify_against_oracle(ref_ids, ref_sc, t.pop("score_matrix"), ids_h, sc_h)
+        if world == 1 and args.cpu_baseline:
+            t, _, _ = reference_step(db_np, q_np, k, sample_q, threads)        # second sample: warm caches
+            cpu_baseline = {
+                "value": extrapolate_qps(t, sample_q, B), "unit": "queries/s", "cores": threads, "kind": "port",
+                "sample": (f"first {sample_q} of {B} queries (one per host thread) vs the full {n}x{d} database on "
+                           f"the host, reference op order (per-call DB re-normalisation {t['normalize_s']:.2f}s, fp32 "
+                           f"GEMM {t['matmul_s']:.2f}s, full stable argsort {t['argsort_s']:.2f}s); QPS extrapolated "
+                           f"to the batch as B/(t_norm + B*(t_gemm+t_sort)/{sample_q}); NumPy port of the reference "
+                           f"(mlx not installable)"),
+                "optimized_cpu": optimized_cpu_line(db_np, q_np, k, sample_q, threads, B),
+            }
+        del db_np, limiter
 
     if rank == 0:
         line = {
@@ -688,7 +803,11 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": f"{args.workload} fp32 cosine top-{k}, batch {B}", "rows": n, "dim": d,
                        "batch": B, "k": k, "sharding": f"rows/{world}", "search_mode": args.mode,
-                       "l2_policy": "database (5.1 GB fp32 + 2.6 GB bf16) is far larger than the 126 MB L2; "
+                       "arithmetic": "fp16 tensor-core prefilter (tcgen05, fp32 accumulate) over a 16-bit shadow of the "
+                                     "normalised rows + per-query certified fp32 rescoring: results are the exact fp32 "
+                                     "ones (uncertified queries are re-run through the fp32 scan; counted below)",
+                       "pipeline": "2 batches in flight (submit i+1, then collect i): ShardedVectorStore.submit/result",
+                       "l2_policy": "database (5.1 GB fp32 + 2.6 GB 16-bit) is far larger than the 126 MB L2; "
                                     "no flush needed between steps",
                        "data_detail": f"{'U[0,1)' if args.dist == 'uniform' else 'N(0,1)'} rows, 8 seeded blocks "
                                       f"(seed 1234+b), queries seed 4321",
@@ -700,9 +819,12 @@ def run_b200(args):
             "clocks": main["clocks"],
             "roofline": main.get("roofline"),
             "cpu_baseline": cpu_baseline,
+            "verified": verified,
             "workloads": extras,
         }
         print(json.dumps(line), flush=True)
+        if verified is not None and not verified["ok"]:
+            raise SystemExit(f"--verify failed: {verified}")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

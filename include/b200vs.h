@@ -52,9 +52,10 @@ extern "C" {
 #define VS_SHADOW_FP8   2   /* additional e4m3 copy (cosine only) for VS_SEARCH_GEMM_FP8; may be OR-ed */
 
 /* search flags */
-#define VS_SEARCH_AUTO        0   /* one query: K2 fp32 scan; two or more: K3 (when the store
-                                     has the 16-bit shadow, cosine / dot_product, k <= 128,
-                                     >= 65536 rows, no row mask), else K2                    */
+#define VS_SEARCH_AUTO        0   /* K3 (certified exact) when the store has the 16-bit shadow,
+                                     k <= 128, >= 65536 rows and a row mask (if any) keeps at
+                                     least a fifth of them -- euclidean: for two or more
+                                     queries --, else the K2 fp32 scan                        */
 #define VS_SEARCH_SCAN_FP32   1   /* K2: fp32 streaming scan (exact)                        */
 #define VS_SEARCH_SCAN_BF16   2   /* K2 over the 16-bit shadow + K5 fp32 rescoring (recall) */
 #define VS_SEARCH_GEMM        3   /* K3: tcgen05 16-bit GEMM candidates + K5 rescoring,
@@ -129,16 +130,38 @@ VS_API int vs_read_rows(vs_store* s, int64_t first, int64_t m, float* out, int o
  * q: (B, dim) fp32 row-major DEVICE pointer.  out_scores / out_ids: (B, k) DEVICE pointers.
  * Row b holds min(k, count) results, best first; remaining slots id -1.
  * `row_mask` (nullable): device bitmap, bit i of word i/32 set = row i takes part
- * (the metadata filter of :159-167 pushed into the scan). */
+ * (the metadata filter of :159-167 pushed into the scan / the GEMM epilogue); `mask_live` = its
+ * number of set bits (-1 = unknown: the search then takes the masked scan; ignored without a mask).
+ * The work is enqueued on `stream`; a certified GEMM search (VS_SEARCH_GEMM, and AUTO when it
+ * picks K3) additionally WAITS on the host for its certification count (one int per 2048
+ * queries) and, when a query could not be certified, re-runs it before returning.  Use
+ * vs_search_submit / vs_search_complete to keep that wait off the critical path. */
 VS_API int vs_search(vs_store* s, const float* q, int B, int k, int flags,
-                     const uint32_t* row_mask, float* out_scores, int32_t* out_ids,
-                     void* stream);
+                     const uint32_t* row_mask, int64_t mask_live, float* out_scores,
+                     int32_t* out_ids, void* stream);
+
+/* The same search split in two so that a caller can keep several batches in flight:
+ *   vs_search_submit    enqueues every kernel of the search on `stream` and returns without
+ *                       waiting for the GPU (the certification count travels to pinned host
+ *                       memory behind the last kernel);
+ *   vs_search_complete  waits for THAT search's count only, re-runs the queries that could not
+ *                       be certified (enqueued on the same stream, results land in the same
+ *                       output rows) and frees the ticket.  In the common case (count 0) it
+ *                       enqueues nothing.
+ * `q`, `row_mask` and the output buffers must stay valid and unmodified until
+ * vs_search_complete returns; the results are final (in stream order) only after it.
+ * New in this engine (the reference is synchronous, service/optimized_vector_store.py:116-192). */
+typedef struct vs_ticket vs_ticket;
+VS_API int vs_search_submit(vs_store* s, const float* q, int B, int k, int flags,
+                            const uint32_t* row_mask, int64_t mask_live, float* out_scores,
+                            int32_t* out_ids, void* stream, vs_ticket** ticket_out);
+VS_API int vs_search_complete(vs_store* s, vs_ticket* ticket);
 
 /* Same with HOST buffers: H2D of the queries, search, D2H of the results, stream
  * synchronised on return.  This is the call MLXVectorStore.query()/batch_query() make. */
 VS_API int vs_search_host(vs_store* s, const float* q_host, int B, int k, int flags,
-                          const uint32_t* row_mask_dev, float* out_scores_host,
-                          int32_t* out_ids_host);
+                          const uint32_t* row_mask_dev, int64_t mask_live,
+                          float* out_scores_host, int32_t* out_ids_host);
 
 /* Per-query certification flags of the last VS_SEARCH_GEMM call on this store/stream are
  * folded into the result (uncertified queries are re-run exactly); this returns how many

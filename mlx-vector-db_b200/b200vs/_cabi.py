@@ -36,11 +36,13 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+    path = Path(os.environ.get("B200VS_LIB") or LIB_PATH)     # diagnostic: A/B-test another build of the library
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m b200vs.build` "
+            f"{path} is missing: build it with `python -m b200vs.build` "
             "(this engine has no CPU fallback)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     p, i32, i64, f32p, i32p, u32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p
     sig = {
         "vs_last_error": (C.c_char_p, []),
@@ -56,8 +58,10 @@ def lib() -> C.CDLL:
         "vs_reset": (i32, [p]),
         "vs_memory_bytes": (i64, [p]),
         "vs_read_rows": (i32, [p, i64, i64, f32p, i32, p]),
-        "vs_search": (i32, [p, f32p, i32, i32, i32, u32p, f32p, i32p, p]),
-        "vs_search_host": (i32, [p, f32p, i32, i32, i32, u32p, f32p, i32p]),
+        "vs_search": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p, p]),
+        "vs_search_submit": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p, p, C.POINTER(p)]),
+        "vs_search_complete": (i32, [p, p]),
+        "vs_search_host": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p]),
         "vs_fallback_count": (i64, [p]),
         "vs_retry_count": (i64, [p]),
         "vs_merge": (i32, [i32, i32, f32p, i32p, i32, i32, i32, i64, f32p, i32p, p]),

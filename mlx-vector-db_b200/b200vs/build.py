@@ -32,8 +32,6 @@ if os.environ.get("B200VS_RES_TN"):          # diagnostic: K3 RESIDENT tile widt
     NVCC_FLAGS.append("-DVS_RES_TN=" + os.environ["B200VS_RES_TN"])
 if os.environ.get("B200VS_RES_ISSUERS"):     # diagnostic: MMA-issuing warps of K3 RESIDENT (1 | 2)
     NVCC_FLAGS.append("-DVS_RES_ISSUERS=" + os.environ["B200VS_RES_ISSUERS"])
-if os.environ.get("B200VS_RARE_REGS"):       # experimental: register-based rare path of K3's filter epilogue
-    NVCC_FLAGS.append("-DVS_RARE_REGS=" + os.environ["B200VS_RARE_REGS"])
 if os.environ.get("B200VS_DEBUG_BUILD") == "1":
     NVCC_FLAGS.append("-DVS_GEMM_DEBUG_MODES")
 
@@ -61,6 +59,10 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     file lock serialises the builders, later ones find the stamp up to date, and the library is
     moved into place atomically so a reader never sees a half-written file."""
     import fcntl
+    # B200VS_SKIP_BUILD=1: use the library as shipped (GPU boxes get the .so built here with the
+    # snapshot; a source edit racing the snapshot must not trigger a rebuild there)
+    if os.environ.get("B200VS_SKIP_BUILD") == "1" and LIB.exists() and not force:
+        return LIB
     BUILD.mkdir(exist_ok=True)
     with open(BUILD / "lock", "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)

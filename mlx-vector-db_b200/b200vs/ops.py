@@ -200,7 +200,7 @@ def _search(q2d: torch.Tensor, db: torch.Tensor, k: int) -> Tuple[torch.Tensor, 
     h = _db_cache.get(db)
     ids = torch.empty((B, kk), dtype=torch.int32, device=db.device)
     scores = torch.empty((B, kk), dtype=torch.float32, device=db.device)
-    _cabi.check(_cabi.lib().vs_search(h, _ptr(q2d), B, kk, _cabi.SEARCH_AUTO, None, _ptr(scores),
+    _cabi.check(_cabi.lib().vs_search(h, _ptr(q2d), B, kk, _cabi.SEARCH_AUTO, None, -1, _ptr(scores),
                                       _ptr(ids), _stream(db)))
     return ids, scores
 

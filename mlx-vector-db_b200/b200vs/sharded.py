@@ -30,6 +30,7 @@ class NativeShard:
         if device.type != "cuda":
             raise RuntimeError("b200vs shards live on CUDA devices only (no CPU fallback)")
         self.device = device
+        self.dimension = dimension
         self.metric = _cabi.METRICS[metric]
         self.flags = _cabi.SEARCH_MODES[search_mode]
         self.handle = C.c_void_p()
@@ -61,9 +62,52 @@ class NativeShard:
     def search_into(self, q: torch.Tensor, k: int, pack: torch.Tensor) -> None:
         """pack[0] <- fp32 scores (bit pattern), pack[1] <- int32 global ids; (B, k) each."""
         B = q.shape[0]
-        _cabi.check(_cabi.lib().vs_search(self.handle, C.c_void_p(q.data_ptr()), B, k, self.flags, None,
+        _cabi.check(_cabi.lib().vs_search(self.handle, C.c_void_p(q.data_ptr()), B, k, self.flags, None, -1,
                                           C.c_void_p(pack[0].data_ptr()), C.c_void_p(pack[1].data_ptr()),
                                           self._stream()))
+
+    def submit_into(self, q: torch.Tensor, k: int, pack: torch.Tensor, row_mask=None,
+                    mask_live: int = -1) -> C.c_void_p:
+        """`search_into` without the host wait: everything is enqueued, the certification check
+        stays pending in the returned ticket until `complete` (vs_search_submit).
+        row_mask: int32 device bitmap over this shard's LOCAL rows (make_row_mask)."""
+        ticket = C.c_void_p()
+        _cabi.check(_cabi.lib().vs_search_submit(
+            self.handle, C.c_void_p(q.data_ptr()), q.shape[0], k, self.flags,
+            None if row_mask is None else C.c_void_p(row_mask.data_ptr()), int(mask_live),
+            C.c_void_p(pack[0].data_ptr()), C.c_void_p(pack[1].data_ptr()), self._stream(), C.byref(ticket)))
+        return ticket
+
+    def make_row_mask(self, hit: np.ndarray) -> torch.Tensor:
+        """bool (local rows,) -> device bitmap (whole 32-bit words + one spare word)."""
+        bits = np.packbits(hit, bitorder="little")
+        buf = np.zeros(((hit.shape[0] + 31) // 32 + 1) * 4, np.uint8)
+        buf[:bits.size] = bits
+        mask = torch.from_numpy(buf.view(np.int32)).to(self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        return mask
+
+    def reset(self) -> None:
+        _cabi.check(_cabi.lib().vs_reset(self.handle))
+
+    def memory_bytes(self) -> int:
+        return int(_cabi.lib().vs_memory_bytes(self.handle))
+
+    def read_rows(self, first: int, m: int) -> np.ndarray:
+        out = np.empty((m, self.dimension), np.float32)
+        if m:
+            _cabi.check(_cabi.lib().vs_read_rows(self.handle, first, m, out.ctypes.data_as(C.c_void_p), 0, None))
+        return out
+
+    def complete(self, ticket) -> None:
+        lib = _cabi.lib()
+        before = lib.vs_retry_count(self.handle) + lib.vs_fallback_count(self.handle)
+        _cabi.check(lib.vs_search_complete(self.handle, ticket))
+        self._completed_launches = lib.vs_retry_count(self.handle) + lib.vs_fallback_count(self.handle) - before
+
+    def last_complete_enqueued_work(self) -> bool:
+        """True when the last `complete` had to re-run uncertified queries (kernels enqueued)."""
+        return bool(getattr(self, "_completed_launches", 0))
 
     def merge(self, gathered: torch.Tensor, G: int, B: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """gathered: (G, 2, B, k) int32 as produced by the all-gather of `pack`."""
@@ -85,6 +129,14 @@ class NativeShard:
         if self.handle.value:
             _cabi.lib().vs_destroy(self.handle)
             self.handle = C.c_void_p()
+
+
+class PendingSearch:
+    """Handle returned by ShardedVectorStore.submit()."""
+    __slots__ = ("q", "B", "kk", "bufs", "ticket", "done")
+
+    def __init__(self, q, B, kk, bufs, ticket, done=None):
+        self.q, self.B, self.kk, self.bufs, self.ticket, self.done = q, B, kk, bufs, ticket, done
 
 
 def split_batch(m: int, world: int, rank: int) -> Tuple[int, int]:
@@ -117,6 +169,10 @@ class ShardedVectorStore:
         self.shard = factory(dimension, metric, device, shadow_bf16, max_vectors_per_shard, search_mode)
         self.total = 0
         self._bufs = {}
+        self._xstream = None
+        # searches that may be in flight between submit() and result(); their buffers are recycled
+        # in a ring of this depth
+        self.pipeline_depth = 4
         # B200VS_SHARD_SYNC=1: synchronise the stream before returning (measured: no effect on throughput)
         import os
         self.sync_each_search = (self.world > 1 and device.type == "cuda" and
@@ -145,7 +201,19 @@ class ShardedVectorStore:
     # ------------------------------------------------------------------ search
     def search(self, queries, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         """(ids (B, kk) int32, scores (B, kk) fp32) on this rank's device, kk = min(k, total);
-        identical on every rank and to an unsharded store."""
+        identical on every rank and to an unsharded store.  = result(submit(...))."""
+        return self.result(self.submit(queries, k))
+
+    def reset(self) -> None:
+        """Forget all rows on every rank (MLXVectorStore.clear's in-memory part)."""
+        self.shard.reset()
+        self.total = 0
+
+    def submit(self, queries, k: int = 10, row_mask=None, mask_live: int = -1) -> "PendingSearch":
+        """Enqueue this rank's local search (K2/K3 -> local top-k with global ids) on the current
+        stream without waiting for the GPU; `result` finishes it.  Several searches may be in
+        flight (a server keeps the GPU busy with batch i+1 while batch i's certification count
+        travels to the host and its candidates cross NVLink); results come back in submit order."""
         q = self.shard.prepare_queries(queries)
         if q.ndim == 1:
             q = q.reshape(1, -1)
@@ -154,28 +222,72 @@ class ShardedVectorStore:
         B = q.shape[0]
         kk = max(0, min(int(k), self.total))
         if B == 0 or kk == 0:
-            return (torch.zeros((B, 0), dtype=torch.int32, device=q.device),
-                    torch.zeros((B, 0), dtype=torch.float32, device=q.device))
-        # The buffers the collective touches are kept per (B, k) instead of being re-allocated:
-        # tensors used on NCCL's stream go back to torch's caching allocator only after that
-        # stream has passed them, so a host that runs ahead of the GPU would otherwise fall
-        # through to cudaMalloc (a device-wide synchronisation) every few steps.
+            return PendingSearch(q, B, kk, None, None)
+        # The buffers the collective touches are kept per (B, k) in a small ring instead of being
+        # re-allocated: tensors used on NCCL's stream go back to torch's caching allocator only
+        # after that stream has passed them, so a host that runs ahead of the GPU would otherwise
+        # fall through to cudaMalloc (a device-wide synchronisation) every few steps.
         key = (B, kk)
-        bufs = self._bufs.get(key)
-        if bufs is None:
-            pack = self.shard.new_pack(B, kk)
-            flat = torch.empty((self.world * pack.numel(),), dtype=pack.dtype, device=pack.device)
+        ring = self._bufs.get(key)
+        if ring is None:
             if len(self._bufs) > 8:
                 self._bufs.clear()
-            bufs = self._bufs[key] = (pack, flat)
-        pack, flat = bufs
-        self.shard.search_into(q, kk, pack)
+            ring = self._bufs[key] = {"slots": [], "next": 0}
+        if len(ring["slots"]) < self.pipeline_depth:
+            pack = self.shard.new_pack(B, kk)
+            flat = torch.empty((self.world * pack.numel(),), dtype=pack.dtype, device=pack.device) \
+                if self.world > 1 else None
+            ring["slots"].append((pack, flat))
+        pack, flat = ring["slots"][ring["next"] % len(ring["slots"])]
+        ring["next"] += 1
+        if row_mask is not None and mask_live == 0:
+            # no local row takes part: this rank contributes an empty candidate block
+            pack[0].zero_()
+            pack[1].fill_(-1)
+            ticket = None
+        elif row_mask is not None:
+            ticket = self.shard.submit_into(q, kk, pack, row_mask, mask_live)
+        else:
+            ticket = self.shard.submit_into(q, kk, pack)
+        done = None
+        if self.world > 1 and self.device.type == "cuda":
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+        return PendingSearch(q, B, kk, (pack, flat), ticket, done)
+
+    def result(self, pending: "PendingSearch") -> Tuple[torch.Tensor, torch.Tensor]:
+        """Finish a submitted search: wait for ITS certification count (re-running what could not
+        be certified), then one all-gather of the packed (2, B, k) block per rank and the K4 merge,
+        both on a side stream so the searches enqueued behind it are not held up."""
+        q, B, kk = pending.q, pending.B, pending.kk
+        if pending.bufs is None:
+            return (torch.zeros((B, 0), dtype=torch.int32, device=q.device),
+                    torch.zeros((B, 0), dtype=torch.float32, device=q.device))
+        pack, flat = pending.bufs
+        if pending.ticket is not None:
+            self.shard.complete(pending.ticket)
         if self.world == 1:
             return pack[1].clone(), pack[0].view(torch.float32).clone()
-        dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
-        out = self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
+        if self.device.type != "cuda":          # CPU stand-in shards (gloo tests)
+            dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
+            return self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
+        cur = torch.cuda.current_stream(self.device)
+        if self._xstream is None:
+            self._xstream = torch.cuda.Stream(self.device)
+        xs = self._xstream
+        # a query that was re-run wrote its rows after `done` was recorded: order after those too
+        if self.shard.last_complete_enqueued_work():
+            xs.wait_stream(cur)
+        else:
+            xs.wait_event(pending.done)
+        with torch.cuda.stream(xs):
+            dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
+            out = self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
+        cur.wait_stream(xs)      # the caller consumes the results on its own stream
+        for t in out:
+            t.record_stream(cur)
         if self.sync_each_search:
-            torch.cuda.current_stream(self.device).synchronize()
+            cur.synchronize()
         return out
 
     def close(self) -> None:

@@ -15,6 +15,7 @@ import json
 import logging
 import shutil
 import threading
+from array import array
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Tuple
@@ -58,8 +59,51 @@ def _to_host_f32(x) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(x, dtype=np.float32))
 
 
+class _MetadataIndex:
+    """Exact-match index over the metadata list: (key, value) -> row ids, built incrementally at
+    `add_vectors`, so that a filter becomes a few vectorised set operations instead of the
+    reference's Python predicate over all N dicts per query
+    (service/optimized_vector_store.py:159-167).  Semantics are the reference's
+    `all(meta.get(key) == val ...)`: a row without the key has the value None.  Values that
+    cannot be hashed (or NaN, which never equals itself) are left to the generic predicate."""
+
+    def __init__(self):
+        self._rows: Dict[Any, Dict[Any, array]] = {}
+        self._generic_keys = set()          # keys that hold an unhashable value somewhere
+
+    def extend(self, first_row: int, metadata: List[Dict]):
+        for r, meta in enumerate(metadata, start=first_row):
+            for key, val in meta.items():
+                try:
+                    if val != val:              # NaN
+                        raise TypeError
+                    self._rows.setdefault(key, {}).setdefault(val, array("q")).append(r)
+                except TypeError:
+                    self._generic_keys.add(key)
+
+    def lookup(self, n_rows: int, key, val) -> Optional[np.ndarray]:
+        """bool (n_rows,) hit vector for `meta.get(key) == val`, or None when this pair needs
+        the generic predicate."""
+        if key in self._generic_keys:
+            return None
+        try:
+            if val is None or val != val:
+                return None
+            ids = self._rows.get(key, {}).get(val)
+        except TypeError:
+            return None
+        hit = np.zeros(n_rows, dtype=np.bool_)
+        if ids is not None and len(ids):
+            idx = np.frombuffer(ids, dtype=np.int64)
+            hit[idx[idx < n_rows]] = True
+        return hit
+
+
 class MLXVectorStore:
-    """Flat (N, D) fp32 store resident in HBM; exact brute-force top-k search."""
+    """Flat (N, D) fp32 store resident in HBM; exact brute-force top-k search.
+
+    Limits (the reference has none because it sorts all N scores): k <= 1024 per query
+    (larger k raises ValueError), N < 2**31 rows."""
 
     def __init__(self, store_path: str, config: Optional[MLXVectorStoreConfig] = None):
         self.store_path = Path(store_path).expanduser()
@@ -67,9 +111,11 @@ class MLXVectorStore:
         self._lock = threading.RLock()
         self.store_path.mkdir(parents=True, exist_ok=True)
         self._metadata: List[Dict] = []
+        self._index = _MetadataIndex()
         self._vector_count = 0
+        self._version = 0                 # bumped by every add / clear: invalidates cached bitmaps
+        self._mask_cache: Dict[Any, Tuple[int, Any, int]] = {}
         self._handle = C.c_void_p()
-        self._segments = 0
         if self.config.enable_hnsw:
             logger.warning("enable_hnsw=True ignored: this engine serves exact search only")
         # reference :211-213 -- only cosine / euclidean get a score function, and only with
@@ -106,31 +152,49 @@ class MLXVectorStore:
     def add_vectors(self, vectors, metadata: List[Dict]):
         """service/optimized_vector_store.py:96-114.  Appends in place (K1); no O(N) copy."""
         with self._lock:
-            if _is_torch(vectors) and vectors.is_cuda:
+            on_device = _is_torch(vectors) and vectors.is_cuda
+            if on_device:
                 v = vectors.detach().to(torch.float32).contiguous()
                 if v.ndim == 1:
                     v = v.reshape(1, -1)
-                self._check_dim(v.shape)
-                stream = torch.cuda.current_stream(v.device).cuda_stream
-                _cabi.check(_cabi.lib().vs_append(self._handle, C.c_void_p(v.data_ptr()),
-                                                  v.shape[0], 1, C.c_void_p(stream)))
                 host_rows = None
-                m = v.shape[0]
             else:
-                host_rows = _to_host_f32(vectors)
-                if host_rows.ndim == 1:
-                    host_rows = host_rows.reshape(1, -1)
-                self._check_dim(host_rows.shape)
-                m = host_rows.shape[0]
-                _cabi.check(_cabi.lib().vs_append(self._handle, host_rows.ctypes.data_as(C.c_void_p),
-                                                  m, 0, None))
+                v = host_rows = _to_host_f32(vectors)
+                if v.ndim == 1:
+                    v = host_rows = v.reshape(1, -1)
+            self._check_dim(v.shape)
+            m = int(v.shape[0])
+            metadata = list(metadata)
+            if len(metadata) != m:
+                # the reference extends its list with whatever it is given (:104) and then serves
+                # wrong or missing metadata; keep one entry per row instead
+                logger.warning("%d vectors but %d metadata entries: %s", m, len(metadata),
+                               "padding with {}" if len(metadata) < m else "dropping the surplus")
+                metadata = metadata[:m] + [{} for _ in range(m - len(metadata))]
+            # metadata first: a concurrent (lock-free, like the reference's) query never sees a
+            # row id without its metadata entry
+            first = len(self._metadata)
             self._metadata.extend(metadata)
+            try:
+                if on_device:
+                    stream = torch.cuda.current_stream(v.device).cuda_stream
+                    _cabi.check(_cabi.lib().vs_append(self._handle, C.c_void_p(v.data_ptr()), m, 1,
+                                                      C.c_void_p(stream)))
+                else:
+                    _cabi.check(_cabi.lib().vs_append(self._handle, host_rows.ctypes.data_as(C.c_void_p),
+                                                      m, 0, None))
+            except Exception:
+                del self._metadata[first:]
+                raise
+            self._index.extend(first, metadata)
             self._vector_count = int(_cabi.lib().vs_count(self._handle))
+            self._version += 1
+            self._mask_cache.clear()
             if self.config.persist:
                 if host_rows is None:
                     host_rows = self._read_rows(self._vector_count - m, m)
-                self._persist_append(host_rows, list(metadata))
-            return {"vectors_added": len(metadata), "total_vectors": self._vector_count}
+                self._persist_append(first, host_rows, metadata)
+            return {"vectors_added": m, "total_vectors": self._vector_count}
 
     def _check_dim(self, shape):
         if len(shape) != 2 or shape[1] != self.config.dimension:
@@ -166,8 +230,10 @@ class MLXVectorStore:
         return self._search_host(q, k, filter_metadata)
 
     def search_arrays(self, queries: np.ndarray, k: int = 10, flags: Optional[int] = None,
-                      row_mask=None) -> Tuple[np.ndarray, np.ndarray]:
-        """(ids (B, k) int32, scores (B, k) fp32) as arrays; unused slots id -1."""
+                      row_mask=None, mask_live: int = -1) -> Tuple[np.ndarray, np.ndarray]:
+        """(ids (B, k) int32, scores (B, k) fp32) as arrays; unused slots id -1.
+        row_mask: int32 device tensor, bit i of word i/32 = row i takes part; mask_live = its
+        popcount (lets AUTO use the tensor-core path for the filtered search)."""
         q = _to_host_f32(queries)
         if q.ndim == 1:
             q = q.reshape(1, -1)
@@ -182,43 +248,88 @@ class MLXVectorStore:
             mask_ptr = C.c_void_p(row_mask.data_ptr())
         _cabi.check(_cabi.lib().vs_search_host(
             self._handle, q.ctypes.data_as(C.c_void_p), B, k,
-            self._flags() if flags is None else flags, mask_ptr,
+            self._flags() if flags is None else flags, mask_ptr, int(mask_live),
             scores.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p)))
         return ids, scores
+
+    # -- metadata filter -> device bitmap (reference :159-167: exact-match AND over keys) --
+    def _filter_hits(self, filter_metadata: Dict, n_rows: int) -> np.ndarray:
+        hit = None
+        generic = {}
+        for key, val in filter_metadata.items():
+            h = self._index.lookup(n_rows, key, val)
+            if h is None:
+                generic[key] = val
+            else:
+                hit = h if hit is None else (hit & h)
+        if generic:   # unhashable / None / NaN values: the reference's predicate, row by row
+            g = np.fromiter((all(m.get(key) == val for key, val in generic.items())
+                             for m in self._metadata[:n_rows]), dtype=np.bool_, count=n_rows)
+            hit = g if hit is None else (hit & g)
+        return hit
+
+    def _row_mask(self, filter_metadata: Dict):
+        """(device bitmap, rows set) for this filter; cached until the next add / clear.
+        Caller holds the lock."""
+        if torch is None:
+            raise RuntimeError("metadata filters need torch for the device bitmap")
+        try:
+            ckey = tuple(sorted(filter_metadata.items(), key=lambda kv: repr(kv[0])))
+            hash(ckey)
+        except TypeError:
+            ckey = None
+        if ckey is not None:
+            ent = self._mask_cache.get(ckey)
+            if ent is not None and ent[0] == self._version:
+                return ent[1], ent[2]
+        n_rows = self._vector_count
+        hit = self._filter_hits(filter_metadata, n_rows)
+        n_live = int(hit.sum())
+        mask = None
+        if n_live:
+            bits = np.packbits(hit, bitorder="little")
+            # whole 32-bit words, plus one spare word: kernels read the word of their 32-row chunk
+            words = (n_rows + 31) // 32 + 1
+            buf = np.zeros(words * 4, np.uint8)
+            buf[:bits.size] = bits
+            dev = torch.device("cuda", int(self.config.device))
+            mask = torch.from_numpy(buf.view(np.int32)).to(dev)
+            torch.cuda.current_stream(dev).synchronize()     # vs_search_host runs on the store's own stream
+        if ckey is not None:
+            if len(self._mask_cache) >= 16:
+                self._mask_cache.clear()
+            self._mask_cache[ckey] = (self._version, mask, n_live)
+        return mask, n_live
 
     def _search_host(self, q: np.ndarray, k: int, filter_metadata: Optional[Dict]):
         B = q.shape[0]
         k = int(k)
         if k == 0:
             return [([], [], []) for _ in range(B)]
-        row_mask = None
-        n_live = self._vector_count
         if filter_metadata:
-            # reference :159-167: exact-match AND over keys; here the predicate becomes a
-            # device bitmap consumed by the scan instead of a row gather.
-            hit = np.fromiter((all(m.get(key) == val for key, val in filter_metadata.items())
-                               for m in self._metadata), dtype=np.bool_, count=len(self._metadata))
-            n_live = int(hit.sum())
-            if n_live == 0:
+            # The bitmap is built for the rows present now; the lock keeps an append from
+            # growing the store between building it and the search that indexes it.
+            with self._lock:
+                row_mask, n_live = self._row_mask(filter_metadata)
+                if n_live == 0:
+                    return [([], [], []) for _ in range(B)]
+                kk = min(k, n_live) if k > 0 else max(0, n_live + k)
+                if kk == 0:
+                    return [([], [], []) for _ in range(B)]
+                ids, scores = self.search_arrays(q, kk, row_mask=row_mask, mask_live=n_live)
+        else:
+            n_live = self._vector_count
+            # the reference slices `argsort(...)[:k]` (:178,:181): k > N returns N results, a negative
+            # k drops the last |k| of the rows
+            kk = min(k, n_live) if k > 0 else max(0, n_live + k)
+            if kk == 0:
                 return [([], [], []) for _ in range(B)]
-            if torch is None:
-                raise RuntimeError("metadata filters need torch for the device bitmap")
-            bits = np.packbits(hit, bitorder="little")
-            pad = (-bits.size) % 4
-            if pad:
-                bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
-            row_mask = torch.from_numpy(bits.view(np.int32).copy()).to(f"cuda:{self.config.device}")
-            torch.cuda.current_stream(row_mask.device).synchronize()
-        # the reference slices `argsort(...)[:k]` (:178,:181): k > N returns N results, a negative k
-        # drops the last |k| of the (filtered) rows
-        kk = min(k, n_live) if k > 0 else max(0, n_live + k)
-        if kk == 0:
-            return [([], [], []) for _ in range(B)]
-        ids, scores = self.search_arrays(q, kk, row_mask=row_mask)
+            ids, scores = self.search_arrays(q, kk)
+        meta = self._metadata
         out = []
         for b in range(B):
             idx = ids[b].tolist()
-            out.append((idx, scores[b].tolist(), [self._metadata[i] for i in idx]))
+            out.append((idx, scores[b].tolist(), [meta[i] for i in idx]))
         return out
 
     # ------------------------------------------------------------------ misc surface
@@ -230,7 +341,10 @@ class MLXVectorStore:
                     shutil.rmtree(self.store_path)
                 self.store_path.mkdir(parents=True, exist_ok=True)
                 _cabi.check(_cabi.lib().vs_reset(self._handle))
-                self._metadata, self._vector_count, self._segments = [], 0, 0
+                self._metadata, self._vector_count = [], 0
+                self._index = _MetadataIndex()
+                self._version += 1
+                self._mask_cache.clear()
             except Exception as e:  # reference logs and carries on
                 logger.error("clear failed for %s: %s", self.store_path, e)
 
@@ -261,8 +375,11 @@ class MLXVectorStore:
     # ------------------------------------------------------------------ persistence
     # On-disk format is the reference's (service/optimized_vector_store.py:218-239):
     # `vectors.npz` with key `vectors` (N, D) fp32 and `metadata.jsonl`, one JSON object per
-    # row.  Appends additionally write `segments/seg_XXXXXX.npy` so an add costs O(m), not
-    # O(N); `optimize()` folds the segments back into `vectors.npz`.
+    # row.  Appends additionally write `segments/seg_<first row>_<rows>.npy` so an add costs
+    # O(m), not O(N); `optimize()` folds the segments back into `vectors.npz`.  Every file is
+    # written to a temporary name and renamed; a segment names the rows it holds, so after a
+    # crash between the snapshot's rename and the removal of the segments it covers, loading
+    # skips those segments instead of ingesting their rows twice.
     def _read_rows(self, first: int, m: int) -> np.ndarray:
         out = np.empty((m, self.config.dimension), np.float32)
         if m:
@@ -270,26 +387,27 @@ class MLXVectorStore:
                                                  out.ctypes.data_as(C.c_void_p), 0, None))
         return out
 
-    def _persist_append(self, rows: np.ndarray, metadata: List[Dict]):
+    def _persist_append(self, first: int, rows: np.ndarray, metadata: List[Dict]):
         seg_dir = self.store_path / "segments"
         seg_dir.mkdir(exist_ok=True)
-        np.save(seg_dir / f"seg_{self._segments:06d}.npy", rows)
-        self._segments += 1
+        tmp = seg_dir / f"tmp_{first:012d}.npy"
+        np.save(tmp, rows)
+        tmp.replace(seg_dir / f"seg_{first:012d}_{rows.shape[0]}.npy")
         with open(self.store_path / "metadata.jsonl", "a") as f:
-            for m in metadata:
-                f.write(json.dumps(m) + "\n")
+            f.write("".join(json.dumps(m) + "\n" for m in metadata))
 
     def _write_snapshot(self, rows: np.ndarray):
+        mtmp = self.store_path / "metadata.tmp.jsonl"
+        with open(mtmp, "w") as f:
+            for m in self._metadata[:rows.shape[0]]:
+                f.write(json.dumps(m) + "\n")
         tmp = self.store_path / "vectors.tmp.npz"
         np.savez(str(tmp), vectors=rows)
         tmp.replace(self.store_path / "vectors.npz")
+        mtmp.replace(self.store_path / "metadata.jsonl")
         seg_dir = self.store_path / "segments"
         if seg_dir.exists():
             shutil.rmtree(seg_dir)
-        self._segments = 0
-        with open(self.store_path / "metadata.jsonl", "w") as f:
-            for m in self._metadata:
-                f.write(json.dumps(m) + "\n")
 
     def _save_store(self):
         self.optimize()
@@ -297,13 +415,21 @@ class MLXVectorStore:
     def _load_store(self):
         try:
             parts = []
+            covered = 0
             vp = self.store_path / "vectors.npz"
             if vp.exists():
-                parts.append(np.load(str(vp))["vectors"].astype(np.float32, copy=False))
+                snap = np.load(str(vp))["vectors"].astype(np.float32, copy=False)
+                parts.append(snap)
+                covered = snap.shape[0]
             seg_dir = self.store_path / "segments"
-            segs = sorted(seg_dir.glob("seg_*.npy")) if seg_dir.exists() else []
-            parts.extend(np.load(str(s)) for s in segs)
-            self._segments = len(segs)
+            for seg in (sorted(seg_dir.glob("seg_*.npy")) if seg_dir.exists() else []):
+                first, m = (int(x) for x in seg.stem.split("_")[1:3])
+                if first + m <= covered:
+                    continue                 # already inside the snapshot (interrupted optimize())
+                if first != covered:
+                    raise ValueError(f"segment {seg.name} does not continue the store at row {covered}")
+                parts.append(np.load(str(seg)))
+                covered += m
             meta = []
             mp = self.store_path / "metadata.jsonl"
             if mp.exists():
@@ -315,12 +441,22 @@ class MLXVectorStore:
                     self._check_dim(p.shape)
                     _cabi.check(_cabi.lib().vs_append(self._handle, p.ctypes.data_as(C.c_void_p),
                                                       p.shape[0], 0, None))
+            count = int(_cabi.lib().vs_count(self._handle))
+            if len(meta) != count:
+                # e.g. a crash while metadata.jsonl was being appended to: keep the rows usable
+                logger.error("%s: %d vectors but %d metadata entries; %s", self.store_path, count, len(meta),
+                             "padding with {}" if len(meta) < count else "dropping the surplus")
+                meta = meta[:count] + [{} for _ in range(count - len(meta))]
             self._metadata = meta
-            self._vector_count = int(_cabi.lib().vs_count(self._handle))
+            self._index = _MetadataIndex()
+            self._index.extend(0, meta)
+            self._vector_count = count
+            self._version += 1
         except Exception as e:  # reference :237-239: log and start empty
             logger.error("loading %s failed, starting empty: %s", self.store_path, e)
             _cabi.lib().vs_reset(self._handle)
-            self._metadata, self._vector_count, self._segments = [], 0, 0
+            self._metadata, self._vector_count = [], 0
+            self._index = _MetadataIndex()
 
 
 def create_optimized_vector_store(store_path: str, dimension: int = 384, jit_compile: bool = True,

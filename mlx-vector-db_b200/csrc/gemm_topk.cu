@@ -66,9 +66,6 @@ constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
 constexpr int kMaxGroupTiles = 4;        // pass 1: tiles (of one CTA) per maximum
 constexpr int kGlobalCap = 4096;         // candidate slots per query over all CTAs (= K4's capacity)
 constexpr int kMaxQueriesPerLaunch = 2048;
-#ifndef VS_RARE_REGS
-#define VS_RARE_REGS 0                   // 1: experimental register-based rare path of the filter epilogue
-#endif
 #ifndef VS_RES_ISSUERS
 #define VS_RES_ISSUERS 2
 #endif
@@ -87,6 +84,8 @@ struct GemmParams {
   int kchunks;              // K / 64
   int64_t n_rows;           // database rows visible
   int n_tiles;              // database tiles this launch covers (tile = TN rows)
+  int tile_stride;          // launch tile t is database tile (tile_first + t) * tile_stride (pass 1 samples
+  int tile_first;           //   the whole row range with a stride; pass 2 may run as two ranges)
   int m_tiles;              // query tiles in the batch
   int ngroups;              // RESIDENT: query groups (CTA c serves group c % ngroups)
   int nq;                   // live queries
@@ -110,6 +109,9 @@ struct GemmParams {
   int group_tiles;          //   tiles (of one unit) per maximum: kMaxGroupTiles, or 1 when tiles are scarce
   float* dump;              // kModeDump: (nq, dump_ld)
   int64_t dump_ld;
+  const float* sqnorms;     // euclidean: ||x||^2 per row; the epilogue turns the accumulator s into the key
+                            //   2 s - ||x||^2 (= ||q||^2 - d^2: larger = closer).  NULL: key = s
+  const uint32_t* row_mask; // nullable: bit r set = row r takes part (metadata filter pushed into the GEMM)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -185,12 +187,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
 }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -331,6 +327,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t bar_accf = s_u32(bars + 1 + 2 * p.stages);
   const uint32_t bar_acce = s_u32(bars + 1 + 2 * p.stages + SLOTS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * p.stages + 2 * SLOTS);
+  // euclidean only: ||x||^2 of the current tile's rows, per epilogue group, double-buffered
+  float* sq_base = reinterpret_cast<float*>(tail + 512);
 
   // ---- work assignment, in units of one CTA (CG=1) or one CTA pair (CG=2)
   // query tiles are counted per unit: unit tile m covers the 128-row tiles m*CG + crank
@@ -375,7 +373,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       int st = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int nt = uig + i * units_in_group;
+        const int nt = (p.tile_first + uig + i * units_in_group) * p.tile_stride;
         const int row0 = nt * TN + crank * TN_LOCAL;                  // first database row this CTA loads
         if (RES) {
           bar_wait(bar_empty + 8 * st, ph ^ 1u);
@@ -492,8 +490,33 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
     int it = 0;
+    const bool l2 = p.sqnorms != nullptr;
+    const int gtid = threadIdx.x & 127;                 // thread inside its epilogue group
+    float* sq_grp = sq_base + grp * 2 * TN;
+    float sq_next[TN / 128];
+    if (l2 && my_tiles > 0) {
+#pragma unroll
+      for (int h = 0; h < TN / 128; ++h) {
+        const int64_t r = (int64_t)(p.tile_first + uig) * p.tile_stride * TN + h * 128 + gtid;
+        sq_next[h] = r < p.n_rows ? __ldg(p.sqnorms + r) : __int_as_float(0x7f800000);
+      }
+    }
     for (int i = 0; i < my_tiles; ++i) {
-      const int nt = uig + i * units_in_group;
+      const int nt = (p.tile_first + uig + i * units_in_group) * p.tile_stride;
+      const float* sqb = sq_grp + (i & 1) * TN;
+      if (l2) {
+        // rows past the end of the store get ||x||^2 = +inf: their key is -inf in every mode
+#pragma unroll
+        for (int h = 0; h < TN / 128; ++h) sq_grp[(i & 1) * TN + h * 128 + gtid] = sq_next[h];
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        if (i + 1 < my_tiles) {
+#pragma unroll
+          for (int h = 0; h < TN / 128; ++h) {
+            const int64_t r = (int64_t)(p.tile_first + uig + (i + 1) * units_in_group) * p.tile_stride * TN + h * 128 + gtid;
+            sq_next[h] = r < p.n_rows ? __ldg(p.sqnorms + r) : __int_as_float(0x7f800000);
+          }
+        }
+      }
 #pragma unroll 1
       for (int mt = 0; mt < m_count; ++mt, ++it) {
         if ((mt % kEpiGroups) != grp) continue;
@@ -538,6 +561,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
               }
             } else {
+              if (l2) {                                  // warp-uniform: key = 2 s - ||x||^2
+                const float4* sq4 = reinterpret_cast<const float4*>(sqb + cc);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 w = sq4[j4];
+                  v[4 * j4 + 0] = fmaf(2.f, v[4 * j4 + 0], -w.x);
+                  v[4 * j4 + 1] = fmaf(2.f, v[4 * j4 + 1], -w.y);
+                  v[4 * j4 + 2] = fmaf(2.f, v[4 * j4 + 2], -w.z);
+                  v[4 * j4 + 3] = fmaf(2.f, v[4 * j4 + 3], -w.w);
+                }
+              }
+              uint32_t mword = 0xffffffffu;              // rows of this chunk that take part
+              if (p.row_mask != nullptr) {
+                const int64_t r0 = (int64_t)nt * TN + cc;
+                mword = r0 < p.n_rows ? __ldg(p.row_mask + (r0 >> 5)) : 0u;
+                if (MODE == kModeMax) {                  // pass 1 bounds the ks-th best TAKING-PART row
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = (mword >> j) & 1u ? v[j] : VS_NEG_INF;
+                }
+              }
               // maxima of the four 8-column groups (independent 3-input FMNMX trees)
               float g[4];
 #pragma unroll
@@ -549,12 +592,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
               if (MODE == kModeMax) rmax = fmaxf(rmax, m);
               if (FILT && __any_sync(0xffffffffu, m >= t)) {
-#if VS_RARE_REGS
-                // rare path, EXPERIMENTAL (off by default, not yet run on a B200): take the hits
-                // straight from the registers of this chunk instead of re-reading TMEM.  Per
-                // 8-column group one warp-uniform vote; inside, a branch-free hit mask per lane
-                // and a (divergent, almost always single-trip) loop over its set bits that picks
-                // the value with a select chain -- no per-value branches, no tcgen05.ld round trip.
+                // rare path: take the hits straight from the registers of this chunk (no second
+                // tcgen05.ld).  Per 8-column group one warp-uniform vote; inside, a branch-free hit
+                // mask per lane and a (divergent, almost always single-trip) loop over its set bits
+                // that picks the value with a select chain -- no per-value branches.  Measured at
+                // 10 M x 128, batch 1024 (profiles/r02_k3_probe.txt): 1.96 ms vs 2.14 ms per search
+                // with the first version, which re-read the 8-column groups from TMEM.
                 const int lim = (int)min((int64_t)TN, p.n_rows - (int64_t)nt * TN) - cc;   // live columns
                 const int32_t id0 = (int32_t)((int64_t)nt * TN + cc);
 #pragma unroll
@@ -565,6 +608,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                   for (int j = 0; j < 8; ++j) hits |= (v[8 * u + j] >= t ? 1u : 0u) << j;
                   const int live = lim - 8 * u;                       // columns of this group inside the store
                   hits &= live >= 8 ? 0xffu : (live <= 0 ? 0u : (1u << live) - 1u);
+                  hits &= mword >> (8 * u);
                   while (hits) {
                     const int j = __ffs((int)hits) - 1;
                     hits &= hits - 1u;
@@ -578,29 +622,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     ++c;
                   }
                 }
-#else
-                // rare path (warp-uniform): re-read only the 8-column groups that hold a hit
-#pragma unroll 1
-                for (int u = 0; u < 4; ++u) {
-                  const float gu = u == 0 ? g[0] : (u == 1 ? g[1] : (u == 2 ? g[2] : g[3]));
-                  if (!__any_sync(0xffffffffu, gu >= t)) continue;
-                  float w[8];
-                  tc_ld8(taddr + (uint32_t)(cc + 8 * u), w);
-                  tc_wait_ld();
-                  const int64_t r0 = (int64_t)nt * TN + cc + 8 * u;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    if (w[j] >= t && r0 + j < p.n_rows) {
-                      if (c < kCandCap) {
-                        p.cand_score[cbase + c] = w[j];
-                        p.cand_id[cbase + c] = (int32_t)(r0 + j);
-                      }
-                      ++c;
-                    }
-                  }
-                }
-                // the reload waited for every outstanding tcgen05.ld, including the prefetch
-#endif
               }
             }
           }
@@ -665,10 +686,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // rounding-error norm ||u - bf16(u)|| and ||u|| for the certification bound
 __global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int dim, int metric, int ld16,
                                          int rows_padded, __nv_bfloat16* __restrict__ out,
-                                         float* __restrict__ qerr, float* __restrict__ qlen) {
+                                         float* __restrict__ qerr, float* __restrict__ qlen,
+                                         int32_t* __restrict__ overflow, int32_t* __restrict__ gcount) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= rows_padded) return;
+  if (lane == 0 && overflow != nullptr) { overflow[b] = 0; gcount[b] = 0; }   // this search's per-query state
   __nv_bfloat16* dst = out + (size_t)b * ld16;
   if (b >= B) {
     for (int c = lane; c < ld16; c += 32) dst[c] = __float2bfloat16_rn(0.f);
@@ -703,10 +726,12 @@ __global__ void prep_queries_bf16_kernel(const float* __restrict__ q, int B, int
 
 // queries -> e4m3 of 16 * q / max(||q||, 1e-8), padded to (rows_padded, ld8)
 __global__ void prep_queries_fp8_kernel(const float* __restrict__ q, int B, int dim, int ld8, int rows_padded,
-                                        unsigned char* __restrict__ out) {
+                                        unsigned char* __restrict__ out, int32_t* __restrict__ overflow,
+                                        int32_t* __restrict__ gcount) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= rows_padded) return;
+  if (lane == 0 && overflow != nullptr) { overflow[b] = 0; gcount[b] = 0; }
   unsigned char* dst = out + (size_t)b * ld8;
   if (b >= B) {
     for (int c = lane; c < ld8; c += 32) dst[c] = 0;
@@ -720,13 +745,77 @@ __global__ void prep_queries_fp8_kernel(const float* __restrict__ q, int B, int 
     dst[c] = (unsigned char)__nv_cvt_float_to_fp8(c < dim ? src[c] * sc : 0.f, __NV_SATFINITE, __NV_E4M3);
 }
 
-// K5 + final K4 + certification in one launch: one CTA per query.
-//   warp 0 prepares the query exactly like prep_queries_kernel (so the scores below are bit-
-//   identical to K2's), the 8 warps rescore the kc candidates in exact fp32 with K2's
-//   accumulation order, warp 0 orders them by (key desc, id asc), writes the top k and decides
-//   whether the candidate set provably contains the exact top-k:
-//       |exact - 16bit| <= ||u|| * max||v - v^|| + ||u - u^|| * max||v^|| + slack =: E
-//       certified  <=>  exact k-th  >  beta + E,   beta = 16-bit score no outside row exceeds
+// tau[q] = the ks-th largest of query q's pass-1 group maxima (-inf with fewer than ks groups).
+// One warp per query: the values are staged in shared memory and the answer is built bit by bit
+// on the order-preserving uint32 encoding (32 counting rounds), so the cost does not depend on
+// the data.  Also clears this search's uncertified-query counter.
+constexpr int kTauWarps = 4;
+__global__ void __launch_bounds__(kTauWarps * 32)
+tau_select_kernel(const float* __restrict__ gmax, int n_groups, int ks, int B, float* __restrict__ tau,
+                  int32_t* __restrict__ bad) {
+  extern __shared__ uint32_t tsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bad != nullptr) bad[0] = 0;
+  const int b = blockIdx.x * kTauWarps + warp;
+  if (b >= B) return;
+  uint32_t* v = tsm + (size_t)warp * n_groups;
+  const float* src = gmax + (int64_t)b * n_groups;
+  for (int i = lane; i < n_groups; i += 32) v[i] = enc_key(src[i]);
+  __syncwarp();
+  uint32_t T = 0;
+  if (n_groups >= ks) {
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < n_groups; i += 32) c += v[i] >= cand;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= ks) T = cand;
+    }
+  }
+  if (lane == 0) tau[b] = n_groups >= ks ? dec_key(T) : VS_NEG_INF;
+}
+
+// Between the two ranges of pass 2: the survivors of the first range (every row of it at or above
+// tau) are a far larger sample than pass 1's, so their ks-th largest key is a tighter -- and still
+// valid -- lower bound of the ks-th best key overall; the second range filters against it.
+// One warp per query over its dense survivor list.
+__global__ void __launch_bounds__(kTauWarps * 32)
+tau_refine_kernel(const float* __restrict__ glist_s, const int32_t* __restrict__ gcount, int ks, int B,
+                  float* __restrict__ tau) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kTauWarps + warp;
+  if (b >= B) return;
+  const int n = min(gcount[b], kGlobalCap);
+  if (n < ks) return;
+  const float* v = glist_s + (int64_t)b * kGlobalCap;
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+    for (int i = lane; i < n; i += 32) c += enc_key(v[i]) >= cand;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= ks) T = cand;
+  }
+  if (lane == 0) tau[b] = fmaxf(tau[b], dec_key(T));
+}
+
+// Candidate selection + K5 + final ordering + certification in ONE launch, one CTA per query.
+//   1. the query's filter survivors (dense list written by pass 2) are staged in shared memory
+//      and the kc best by 16-bit key are selected (bitwise search for the kc-th largest key
+//      beta, then compaction);
+//   2. warp 0 prepares the query exactly like prep_queries_kernel, the 8 warps rescore the
+//      candidates in exact fp32 with K2's accumulation order (bit-identical scores);
+//   3. the candidates are ranked by (key desc, global id asc) by counting; the top k are written;
+//   4. certification: with u the prepared query, v a prepared row and u^, v^ their 16-bit
+//      roundings,  |u.v - u^.v^| <= ||u|| max||v - v^|| + ||u - u^|| max||v^|| + slack.
+//        cosine / dot : key16 = u^.v^            E = that bound
+//                       certified  <=>  exact k-th  >  beta + E
+//        euclidean    : key16 = 2 u^.v^ - ||v||^2 = ||u||^2 - d^2 up to E = 2 * that bound (+ the
+//                       fp32 rounding of ||v||^2, ||u||^2 and d^2, folded into slack)
+//                       certified  <=>  d_k^2  <  ||u||^2 - beta - E
+//      beta = the kc-th candidate's 16-bit key, or tau when fewer than kc rows passed the filter
+//      (no row outside the candidate set has a 16-bit key above beta).  Queries that cannot be
+//      certified (or whose candidate buffers overflowed) are appended to bad[1..], bad[0] counts them.
 constexpr int kFinishThreads = 256;
 constexpr int kMaxCand = 256;
 
@@ -737,8 +826,9 @@ struct FinishParams {
   const float* rows;         // (n, ld) fp32 master
   const float* norms;
   const int32_t* id_map;     // nullable
-  const float* cand_s;       // (B, kc) 16-bit scores, best first
-  const int32_t* cand_i;     // (B, kc) local ids, -1 = empty
+  const float* glist_s;      // (B, kGlobalCap) survivors of the filter: 16-bit keys
+  const int32_t* glist_i;    //                 local row ids
+  const int32_t* gcount;     // (B,) survivors per query (may exceed kGlobalCap: overflow is set then)
   const float* tau;
   const int32_t* overflow;
   const float* qerr;
@@ -749,76 +839,118 @@ struct FinishParams {
   float* out_s;
   int32_t* out_i;
   int64_t out_stride;
-  int* n_bad;
-  int32_t* bad_list;
+  int32_t* bad;              // [0] = number of uncertified queries, [1 + i] = their indices
 };
 
 __global__ void __launch_bounds__(kFinishThreads)
-finish_kernel(const FinishParams p) {
+select_finish_kernel(const FinishParams p) {
   extern __shared__ __align__(16) unsigned char fsm[];
-  float4* qs = reinterpret_cast<float4*>(fsm);                 // prepared query, ld floats
+  uint32_t* sk = reinterpret_cast<uint32_t*>(fsm);                         // encoded 16-bit keys
+  int* si = reinterpret_cast<int*>(sk + kGlobalCap);
+  float4* qs = reinterpret_cast<float4*>(si + kGlobalCap);                 // prepared query, ld floats
   __shared__ float keys[kMaxCand];
   __shared__ int ids[kMaxCand];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int sel[kMaxCand];
+  __shared__ int wcount[2][kFinishThreads / 32];
+  __shared__ int cnt_hi, cnt_eq, have_sh;
+  __shared__ float kth_sh, qsq_sh;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool l2 = p.metric == VS_METRIC_EUCLIDEAN;
+  const int n = min(p.gcount[b], kGlobalCap);
+  for (int i = tid; i < n; i += kFinishThreads) {
+    sk[i] = enc_key(p.glist_s[(int64_t)b * kGlobalCap + i]);
+    si[i] = p.glist_i[(int64_t)b * kGlobalCap + i];
+  }
+  if (tid == 0) { cnt_hi = 0; cnt_eq = 0; have_sh = 0; kth_sh = VS_NEG_INF; }
   const float* src = p.q + (size_t)b * p.dim;
   if (warp == 0) {
     float acc = 0.f;
     for (int c = lane; c < p.dim; c += 32) { const float v = src[c]; acc = fmaf(v, v, acc); }
-    const float nrm = fmaxf(sqrtf(warp_sum(acc)), 1e-8f);
+    const float tot = warp_sum(acc);
+    const float nrm = fmaxf(sqrtf(tot), 1e-8f);
     float* dst = reinterpret_cast<float*>(qs);
     for (int c = lane; c < p.ld; c += 32) {
       float v = c < p.dim ? src[c] : 0.f;
       dst[c] = p.metric == VS_METRIC_COSINE ? v / nrm : v * 1.f;
     }
+    if (lane == 0) qsq_sh = tot;
   }
   __syncthreads();
-  const int nvec = p.ld >> 2;
-  for (int e = warp; e < p.kc; e += kFinishThreads / 32) {
-    const int id = p.cand_i[(int64_t)b * p.kc + e];
-    float key = VS_NEG_INF;
-    if (id >= 0) {
-      const float4* x = reinterpret_cast<const float4*>(p.rows) + (int64_t)id * nvec;
-      float acc = 0.f;
-      for (int c = lane; c < nvec; c += 32) acc = dot4_acc(acc, ldg_stream(x + c), qs[c]);
-      const float tot = warp_sum(acc);
-      key = p.metric == VS_METRIC_COSINE ? tot / __ldg(p.norms + id) : tot;
+  // ---- 1. the kc best survivors by 16-bit key
+  const bool full = n >= p.kc;
+  uint32_t T = 0;
+  if (full) {
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      for (int i = tid; i < n; i += kFinishThreads) c += sk[i] >= cand;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) wcount[bit & 1][warp] = c;
+      __syncthreads();
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kFinishThreads / 32; ++w) tot += wcount[bit & 1][w];
+      if (tot >= p.kc) T = cand;
     }
-    if (lane == 0) { keys[e] = key; ids[e] = id < 0 ? VS_ID_SENTINEL : (p.id_map ? p.id_map[id] : id); }
+  }
+  for (int i = tid; i < n; i += kFinishThreads)
+    if (!full || sk[i] > T) sel[atomicAdd(&cnt_hi, 1)] = i;
+  __syncthreads();
+  if (full) {
+    const int hi = cnt_hi;                       // < kc: fewer than kc keys exceed the kc-th largest
+    for (int i = tid; i < n; i += kFinishThreads)
+      if (sk[i] == T) { const int pos = hi + atomicAdd(&cnt_eq, 1); if (pos < p.kc) sel[pos] = i; }
   }
   __syncthreads();
-  if (warp != 0) return;
-  // rank by counting: lane handles candidates lane and lane + 32
+  const int nsel = full ? p.kc : n;
+  // ---- 2. exact fp32 scores of the candidates
+  const int nvec = p.ld >> 2;
+  for (int e = warp; e < nsel; e += kFinishThreads / 32) {
+    const int id = si[sel[e]];
+    const float4* x = reinterpret_cast<const float4*>(p.rows) + (int64_t)id * nvec;
+    float acc = 0.f;
+    if (l2) { for (int c = lane; c < nvec; c += 32) acc = sqdiff4_acc(acc, ldg_stream(x + c), qs[c]); }
+    else { for (int c = lane; c < nvec; c += 32) acc = dot4_acc(acc, ldg_stream(x + c), qs[c]); }
+    const float tot = warp_sum(acc);
+    float key;
+    if (p.metric == VS_METRIC_COSINE) key = tot / __ldg(p.norms + id);
+    else if (l2) key = -sqrtf(tot);
+    else key = tot;
+    if (lane == 0) { keys[e] = key; ids[e] = p.id_map ? p.id_map[id] : id; }
+  }
+  __syncthreads();
+  // ---- 3. rank by counting
   float* os = p.out_s + (int64_t)b * p.out_stride;
   int32_t* oi = p.out_i + (int64_t)b * p.out_stride;
   const int kk = (int)(p.n_rows < p.k ? p.n_rows : p.k);
-  float kth = VS_NEG_INF;
-  int have = 0;
-  for (int e = lane; e < p.kc; e += 32) {
-    const float mk = keys[e];
-    const int mi = ids[e];
-    if (mi == VS_ID_SENTINEL) continue;   // (kc <= kMaxCand, checked by the host)
+  if (tid < nsel) {
+    const float mk = keys[tid];
+    const int mi = ids[tid];
     int r = 0;
-    for (int j = 0; j < p.kc; ++j) r += (ids[j] != VS_ID_SENTINEL) && better(keys[j], ids[j], mk, mi);
-    if (r < p.k) { os[r] = mk; oi[r] = mi; }
-    if (r == kk - 1) { kth = mk; have = 1; }
+    for (int j = 0; j < nsel; ++j) r += better(keys[j], ids[j], mk, mi);
+    if (r < p.k) { os[r] = l2 ? -mk : mk; oi[r] = mi; }
+    if (r == kk - 1) { kth_sh = mk; have_sh = 1; }
   }
-  int valid = 0;
-  for (int e = lane; e < p.kc; e += 32) valid += ids[e] != VS_ID_SENTINEL;
-  for (int off = 16; off; off >>= 1) {
-    valid += __shfl_xor_sync(0xffffffffu, valid, off);
-    kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, off));
-    have |= __shfl_xor_sync(0xffffffffu, have, off);
-  }
-  for (int e = (valid < p.k ? valid : p.k) + lane; e < p.out_stride; e += 32) { os[e] = 0.f; oi[e] = -1; }
-  if (lane != 0 || !p.certify) return;
+  for (int e = (nsel < p.k ? nsel : p.k) + tid; e < p.out_stride; e += kFinishThreads) { os[e] = 0.f; oi[e] = -1; }
+  __syncthreads();
+  if (tid != 0 || !p.certify) return;
+  // ---- 4. certification
   const float max_err = __uint_as_float(p.bounds[0]);
   const float max_len = __uint_as_float(p.bounds[1]);
-  const float E = p.qlen[b] * max_err + p.qerr[b] * max_len + p.slack * (1.f + p.qlen[b] * max_len);
-  const bool full = p.cand_i[(int64_t)b * p.kc + p.kc - 1] >= 0;
-  const float beta = full ? p.cand_s[(int64_t)b * p.kc + p.kc - 1] : p.tau[b];
+  const float beta = full ? dec_key(T) : p.tau[b];
   bool ok = p.overflow[b] == 0;
-  if (ok && !(!full && p.n_rows <= p.kc)) ok = have && kth > beta + E;
-  if (!ok) p.bad_list[atomicAdd(p.n_bad, 1)] = b;
+  if (ok && !(!full && p.n_rows <= p.kc)) {
+    const float ql = p.qlen[b];
+    if (l2) {
+      const float E = 2.f * (ql * max_err + p.qerr[b] * max_len) + p.slack * (ql + max_len) * (ql + max_len);
+      const float dk = kth_sh;                       // = -distance of the k-th result
+      ok = have_sh && dk * dk * 1.000001f < qsq_sh - beta - E;
+    } else {
+      const float E = ql * max_err + p.qerr[b] * max_len + p.slack * (1.f + ql * max_len);
+      ok = have_sh && kth_sh > beta + E;
+    }
+  }
+  if (!ok) p.bad[1 + atomicAdd(p.bad, 1)] = b;
 }
 
 __global__ void fill_f32_kernel(float* p, float v, int64_t n) {
@@ -902,8 +1034,11 @@ static int gemm_cta_group(int kchunks) {
 }
 
 // m_tiles: 128-row query tiles, already a multiple of cg
-static void plan_gemm(int kchunks, int m_tiles, int cg, GemmPlan* plan) {
-  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/;
+// l2: reserve the epilogue groups' ||x||^2 buffers (2 per group, TN floats each)
+static void plan_gemm(int kchunks, int m_tiles, int cg, bool l2, GemmPlan* plan) {
+  const size_t sq_res = l2 ? (size_t)kEpiGroupsRes * 2 * kResTN * 4 : 0;
+  const size_t sq_str = l2 ? (size_t)kEpiGroupsStream * 2 * 256 * 4 : 0;
+  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/ - (l2 ? std::max(sq_res, sq_str) : 0);
   const int um_tiles = m_tiles / cg;
   if (kchunks <= 4) {   // K <= 256: resident queries
     int mt = kchunks <= 2 ? 4 : 1;
@@ -913,13 +1048,13 @@ static void plan_gemm(int kchunks, int m_tiles, int cg, GemmPlan* plan) {
     const size_t stage = (size_t)kchunks * (kResTN / cg) * 128;  // kResTN / cg database rows per CTA
     int stages = (int)((limit - a) / stage);
     if (stages > 4) stages = 4;
-    if (stages >= 2) { *plan = {mt, cg, stages, a + stages * stage + 1024 + 512, kResTN}; return; }
+    if (stages >= 2) { *plan = {mt, cg, stages, a + stages * stage + 1024 + 512 + sq_res, kResTN}; return; }
   }
   // streaming: query chunk + this CTA's share of the 256-row database chunk
   const size_t stage = (size_t)(cg == 2 ? 2 : 3) * kChunkBytes;
   int stages = (int)(limit / stage);
   if (stages > 6) stages = 6;
-  *plan = {0, cg, stages, stages * stage + 1024 + 512, 256};
+  *plan = {0, cg, stages, stages * stage + 1024 + 512 + sq_str, 256};
 }
 
 // rows per TMA box of the database operand: RESIDENT CTAs load 128 / cg rows per tile in one
@@ -995,6 +1130,7 @@ static void gemm_units(const GemmPlan& plan, int m_tiles, int n_tiles, int num_s
 static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,
                        int num_sms, int* lists_out, cudaStream_t stream) {
   p.stages = plan.stages;
+  if (p.tile_stride < 1) p.tile_stride = 1;
   p.idesc = instr_desc(kTileM * plan.cg, plan.tn, p.fp16 ? 0 : 1);
   int units, lists;
   gemm_units(plan, p.m_tiles, p.n_tiles, num_sms, &units, &p.ngroups, &lists);
@@ -1020,22 +1156,26 @@ static int gemm_enabled() {
   if (v < 0) { const char* e = getenv("B200VS_GEMM"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
   return v;
 }
-static int gemm_min_batch() {
+// Smallest batch AUTO sends to K3.  Measured on B200 (10M x 128): K3 takes 0.50-0.58 ms for any
+// batch of 1..64 queries (it is HBM-bound on the 16-bit shadow there, 6.5 TB/s), K2 needs 0.88 ms
+// for one query over the fp32 rows and ~4 ms per pass of 8 -- so every cosine / dot_product search
+// goes to K3 (exact by certification); euclidean single queries keep the fp32 scan, whose direct-
+// difference form needs no certification margin.  B200VS_GEMM_MIN_BATCH overrides.
+static int gemm_min_batch(const vs_store* s) {
   static int v = -1;
-  // measured on B200 (10M x 128): K3 takes 0.53-0.58 ms for any batch of 8..64 queries (it is
-  // HBM-bound on the 16-bit shadow there), K2 needs 0.88 ms for one query and ~4 ms per pass of
-  // 8 -- so everything but single queries goes to K3
-  if (v < 0) { const char* e = getenv("B200VS_GEMM_MIN_BATCH"); v = e && *e ? atoi(e) : 2; }
-  return v;
+  if (v < 0) { const char* e = getenv("B200VS_GEMM_MIN_BATCH"); v = e && *e ? atoi(e) : 0; }
+  if (v > 0) return v;
+  return s->metric == VS_METRIC_EUCLIDEAN ? 2 : 1;
 }
 
 // candidates kept for rescoring
 static int cand_count(int kk) { return std::max(2 * kk, kk + 22); }
+// rows the pass-1 threshold is guaranteed to admit (see gemm_block)
+static int sample_rank(int kk) { return kk + std::max(6, kk / 2); }
 
 bool gemm_supported(const vs_store* s, int64_t n, int B, int kk) {
   if (!gemm_enabled() || !s->shadow) return false;
-  if (s->metric == VS_METRIC_EUCLIDEAN) return false;       // L2 candidates: bf16 scan path
-  if (B < gemm_min_batch() || s->dim > 8192) return false;
+  if (B < gemm_min_batch(s) || s->dim > 8192) return false;
   if (cand_count(kk) > kMaxCand) return false;            // k <= 128
   if (n < 65536) return false;                              // small stores: the scan is enough
   return true;
@@ -1059,14 +1199,50 @@ struct Ws {
 };
 
 // exact fp32 scan of selected queries (defined in search.cu)
-int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, float* out_scores,
-                       int32_t* out_ids, int64_t out_stride, cudaStream_t stream);
+int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, const uint32_t* row_mask,
+                       float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream);
 
-// kc_want: candidates kept for rescoring (0 = default for kk); a query that cannot be certified
-// is retried once with 4x the candidates (a wider bf16 margin) before the exact scan takes it
-static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
-                      float* out_scores, int32_t* out_ids, int64_t out_stride, int kc_want, bool fp8,
-                      cudaStream_t stream) {
+// ---- certification slots: what outlives the enqueue of a certified GEMM block until its check.
+// A slot owns a pinned int the uncertified-query count is copied to, the event recorded behind
+// that copy and the device list of uncertified queries; slots are recycled, never freed before
+// vs_destroy.
+static int acquire_slot(vs_store* s, int* out) {
+  std::lock_guard<std::mutex> g(s->slot_mu);
+  for (size_t i = 0; i < s->slots.size(); ++i)
+    if (!s->slots[i].busy) { s->slots[i].busy = true; *out = (int)i; return VS_OK; }
+  vs_store::CertSlot c;
+  VS_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+  VS_CUDA(cudaMallocHost((void**)&c.h_bad, sizeof(int)));
+  VS_CUDA(cudaMalloc((void**)&c.d_bad, (size_t)(1 + kMaxQueriesPerLaunch) * 4));
+  c.busy = true;
+  s->slots.push_back(c);
+  *out = (int)s->slots.size() - 1;
+  return VS_OK;
+}
+static void release_slot(vs_store* s, int slot) {
+  std::lock_guard<std::mutex> g(s->slot_mu);
+  s->slots[slot].busy = false;
+}
+void free_cert_slots(vs_store* s) {
+  for (auto& c : s->slots) {
+    if (c.done) cudaEventDestroy(c.done);
+    if (c.h_bad) cudaFreeHost(c.h_bad);
+    if (c.d_bad) cudaFree(c.d_bad);
+  }
+  s->slots.clear();
+}
+
+static int gemm_block_complete(vs_store* s, const PendingBlock& pb, cudaStream_t stream);
+
+// Enqueue one block: prep -> pass 1 -> tau -> pass 2 -> select/rescore/certify.  Never blocks.
+// certify: the uncertified-query count travels to the slot's pinned int behind the last kernel;
+// *pending describes what gemm_block_complete needs to finish the block.
+// kc_want: candidates kept for rescoring (0 = default for kk).
+static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma,
+                              const uint32_t* row_mask, int64_t n_live, float* out_scores, int32_t* out_ids,
+                              int64_t out_stride, int kc_want, bool fp8, cudaStream_t stream, PendingBlock* pending) {
+  pending->slot = -1;
+  const bool l2 = s->metric == VS_METRIC_EUCLIDEAN;
   // fp8: e4m3 shadow, 128 elements per 128-byte chunk row; otherwise the 16-bit shadow, 64 per row
   const int K = fp8 ? s->ld8 : s->ld16;
   const int kch = fp8 ? K / 128 : K / kChunkK;
@@ -1075,62 +1251,75 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   const int rows_padded = m_tiles * kTileM;
   const int kc = (int)std::min<int64_t>(kc_want > 0 ? kc_want : cand_count(kk), n);
   GemmPlan plan;
-  plan_gemm(kch, m_tiles, cg, &plan);
+  plan_gemm(kch, m_tiles, cg, l2, &plan);
   const int tn = plan.tn;
   const int n_tiles = (int)((n + tn - 1) / tn);
-  // pass-1 sample size.  Pass 1 costs ~0.8 f of a full pass (f = sampled fraction); pass 2 then
-  // sees about kc / f survivors per query, i.e. a fraction 1024 kc / (f N) of its 32x32 chunks
-  // take the rare path (~1.5 chunk times each).  Minimising 0.8 f + 1536 kc / (f N) gives
-  // f = sqrt(1920 kc / N): 8 % at N = 10 M, 22 % at N = 1.25 M (one of 8 shards).  At most 4096
-  // tiles (merge kernel capacity), at least 4 kc, whole tiles only.
-  double f = std::sqrt(1920.0 * kc / (double)n);
+  // pass-1 sample.  tau[q] = the ks-th largest per-group maximum of the sample: ks distinct rows
+  // reach it, so it is a lower bound of the ks-th best 16-bit key of the whole database.  ks only
+  // has to exceed k by a margin (the filter may pass FEWER than kc rows: then no row outside the
+  // candidate set exceeds tau and the certification uses beta = tau); a wide retry (kc_want > 0)
+  // asks for all of its kc candidates.  The filter passes about ks / f rows per query, i.e. a
+  // fraction 1024 ks / (f N) of the 32 x 32 epilogue chunks take the rare path (~r chunk times
+  // each), while pass 1 costs ~0.8 f of a full pass: minimising 0.8 f + r 1024 ks / (f N) gives
+  // f = sqrt(1280 r ks / N); r ~ 0.6 for the register-based rare path (tuned on the B200,
+  // profiles/r02_k3_probe.txt).  At least 4 ks groups, at most 4096 (K4's capacity), whole tiles.
+  // With a row mask only n_live rows take part: the sample must hold enough of THOSE.
+  int ks = kc_want > 0 ? kc : std::min(kc, sample_rank(kk));
+  if (const char* e = getenv("B200VS_GEMM_KS")) { if (*e) ks = std::max(1, std::min(kc, atoi(e))); }   // diagnostic
+  const double live_frac = std::max(1e-9, std::min(1.0, (double)n_live / (double)n));
+  double f = std::sqrt(768.0 * ks / ((double)n * live_frac)) ;
   // K > 256 (STREAMING): the MMAs of a tile take several times longer than its epilogue, so the
-  // rare path is hidden and the sample only has to keep the survivors (about 1.2 kc / f per
-  // query) within the candidate buffers and K4's capacity: f = kc / 1500.
-  if (kch > 4) f = std::min(f, kc / 1500.0);
+  // rare path is hidden and the sample only has to keep the survivors (about 1.2 ks / f per
+  // query) within the candidate buffers (64 per CTA pair and query) and K4's capacity.
+  if (kch > 4) f = std::min(f, ks / (750.0 * live_frac));
   if (const char* e = getenv("B200VS_GEMM_SAMPLE")) { if (*e) f = atof(e); }   // diagnostic override
   if (f > 0.5) f = 0.5;
   if (f < 1.0 / 128) f = 1.0 / 128;
-  // Maxima are taken over groups of kMaxGroupTiles tiles when there are plenty (at most 4096
-  // groups: merge kernel capacity), else per tile; at least 4 kc groups so that the kc best
-  // rows rarely share one.
-  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, 4 * kc),
+  const int full_tiles = (int)(n / tn);
+  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, (int64_t)(4 * ks / live_frac)),
                                        4096 * kMaxGroupTiles);
-  if (s_tiles > (int)(n / tn)) s_tiles = (int)(n / tn);
+  if (s_tiles > full_tiles) s_tiles = full_tiles;
+  // the sample is spread over the whole row range (every `s_stride`-th tile), not a prefix: on a
+  // time-ordered or clustered ingest a prefix can be unlike the rest and give a useless threshold
+  const int s_stride = s_tiles > 0 ? std::max(1, full_tiles / s_tiles) : 1;
   int s_units, s_ngroups, s_lists;
   gemm_units(plan, m_tiles, s_tiles, s->num_sms, &s_units, &s_ngroups, &s_lists);
-  const int gt = s_tiles / kMaxGroupTiles >= 4 * kc ? kMaxGroupTiles : 1;
+  const int gt = s_tiles / kMaxGroupTiles >= 4 * ks ? kMaxGroupTiles : 1;
   const int s_groups = s_lists * (((s_tiles + s_lists - 1) / s_lists + gt - 1) / gt);
-  const bool sampled = s_tiles / gt >= 2 * kc && s_groups <= 4096;
-  // Too few rows for a useful threshold (fewer than 2 kc sample groups): every row would be a
-  // candidate and the per-thread buffers would overflow.  Such a store is small; the exact scan
-  // serves it directly (for the uncertified modes too: its recall is 1).
+  const bool sampled = s_tiles / gt >= 2 * ks && s_groups <= 4096 && live_frac >= 0.2;
+  // Too few rows for a useful threshold (fewer than 2 ks sample groups, or a filter that leaves
+  // less than a fifth of the rows): every row would be a candidate and the per-thread buffers
+  // would overflow.  The exact scan serves such a search directly (for the uncertified modes
+  // too: its recall is 1).
   if (!sampled) {
     s->fallbacks.fetch_add(B);
-    return scan_queries_exact(s, n, q, B, kk, scan_tma, out_scores, out_ids, out_stride, stream);
+    return scan_queries_exact(s, n, q, B, kk, scan_tma, row_mask, out_scores, out_ids, out_stride, stream);
   }
+
+  int slot = -1;
+  if (certify) { if (int rc = acquire_slot(s, &slot)) return rc; }
+  int32_t* bad = certify ? s->slots[slot].d_bad : nullptr;
+  struct SlotGuard {   // an error return before the hand-over gives the slot back
+    vs_store* s; int slot; bool keep = false;
+    ~SlotGuard() { if (slot >= 0 && !keep) release_slot(s, slot); }
+  } guard{s, slot};
 
   const int max_lists = s->num_sms;
   Ws ws;
-  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *c1s, *gls; int32_t *ci, *ccnt, *c1i, *ovf, *bad, *gli, *gcnt; int* nbad;
+  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *gls; int32_t *ci, *ccnt, *ovf, *gli, *gcnt;
   ws.want(&qb, (size_t)rows_padded * K);
   ws.want(&qerr, (size_t)rows_padded);
   ws.want(&qlen, (size_t)rows_padded);
   ws.want(&tau, (size_t)rows_padded);
-  ws.want(&gmax, sampled ? (size_t)rows_padded * s_groups : 1);
+  ws.want(&gmax, (size_t)rows_padded * s_groups);
   ws.want(&cs, (size_t)max_lists * rows_padded * kCandCap);
   ws.want(&ci, (size_t)max_lists * rows_padded * kCandCap);
   ws.want(&ccnt, (size_t)max_lists * rows_padded);
   ws.want(&gls, (size_t)rows_padded * kGlobalCap);
   ws.want(&gli, (size_t)rows_padded * kGlobalCap);
-  ws.want(&c1s, (size_t)B * kc);
-  ws.want(&c1i, (size_t)B * kc);
-  int32_t* zeroed;                       // [overflow | gcount | n_bad], cleared by ONE memset
-  ws.want(&zeroed, (size_t)2 * rows_padded + 1);
-  ws.want(&bad, (size_t)B);
+  ws.want(&ovf, (size_t)rows_padded);      // cleared by the prep kernel, like gcnt
+  ws.want(&gcnt, (size_t)rows_padded);
   if (int rc = ws.alloc(stream)) return rc;
-  ovf = zeroed; gcnt = zeroed + rows_padded; nbad = zeroed + 2 * rows_padded;
-  VS_CUDA(cudaMemsetAsync(zeroed, 0, ((size_t)2 * rows_padded + 1) * 4, stream));
 
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
@@ -1140,10 +1329,10 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
 
   if (fp8)   // (the buffer is sized for 2 bytes per element; e4m3 uses half of it)
     prep_queries_fp8_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, K, rows_padded,
-                                                                     reinterpret_cast<unsigned char*>(qb));
+                                                                     reinterpret_cast<unsigned char*>(qb), ovf, gcnt);
   else
     prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
-                                                                      qerr, qlen);
+                                                                      qerr, qlen, ovf, gcnt);
   count_launch();
   VS_CHECK_LAUNCH();
 
@@ -1151,109 +1340,156 @@ static int gemm_block(vs_store* s, int64_t n, const float* q, int B, int kk, boo
   p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = (fp16 || fp8) ? 1 : 0; p.fp8 = fp8 ? 1 : 0;
   p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
   p.glist_s = gls; p.glist_i = gli; p.gcount = gcnt;
+  p.sqnorms = l2 ? (const float*)s->sqnorms.ptr() : nullptr;
+  p.row_mask = row_mask;
 
   if (plan.mt == 0)   // STREAMING keeps its running candidate counts in global memory
     VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
-  if (sampled) {
-    // pass 1: per-query maxima of the sample tiles -> tau = kc-th largest (a lower bound of
-    // the kc-th best score overall)
-    p.mode = kModeMax; p.n_tiles = s_tiles; p.gmax = gmax; p.group_tiles = gt;
-    if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
-    MergeParams m = {};
-    m.ck = gmax; m.ci = nullptr; m.per_query = s_groups; m.chunk = s_groups; m.chunk_stride = 0;
-    m.query_stride = s_groups; m.list_len = 0; m.k = kc; m.tau = nullptr;
-    m.out_s = c1s; m.out_i = c1i; m.out_stride = kc; m.kth_out = tau;      // tau[b] = kc-th largest
-    if (int rc = launch_merge(m, B, stream)) return rc;
-    // diagnostic (timing only, results are wrong): no row passes the filter, so pass 2 never
-    // takes its rare path
-    if (const char* e = getenv("B200VS_GEMM_TAU_INF")) {
-      if (*e == '1') fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, __builtin_inff(), rows_padded);
-    }
-  } else {
-    // tiny store: no sample, every row is a candidate of the filter (tau = -inf)
-    fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, -__builtin_inff(), rows_padded);
-    count_launch();
-    VS_CHECK_LAUNCH();
+  // pass 1: per-query maxima of the sample tiles -> tau = ks-th largest
+  p.mode = kModeMax; p.n_tiles = s_tiles; p.tile_stride = s_stride; p.gmax = gmax; p.group_tiles = gt;
+  if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
+  tau_select_kernel<<<(B + kTauWarps - 1) / kTauWarps, kTauWarps * 32, (size_t)kTauWarps * s_groups * 4, stream>>>(
+      gmax, s_groups, ks, B, tau, bad);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  // diagnostic (timing only, results are wrong): no row passes the filter, so pass 2 never
+  // takes its rare path
+  if (const char* e = getenv("B200VS_GEMM_TAU_INF")) {
+    if (*e == '1') fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, __builtin_inff(), rows_padded);
   }
   // pass 2: threshold filter over all rows
-  p.mode = kModeFilter; p.n_tiles = n_tiles; p.gmax = nullptr;
+  p.mode = kModeFilter; p.n_tiles = n_tiles; p.tile_stride = 1; p.gmax = nullptr;
 #ifdef VS_GEMM_DEBUG_MODES
   if (const char* e = getenv("B200VS_GEMM_DBGMODE")) { if (*e == '3' || *e == '4') p.mode = atoi(e); }
 #endif
-  if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
-  // K4: best kc candidates by 16-bit (or e4m3) score out of the dense per-query lists
-  {
-    MergeParams m = {};
-    m.ck = gls; m.ci = gli; m.per_query = kGlobalCap; m.chunk = kGlobalCap;
-    m.chunk_stride = 0; m.query_stride = kGlobalCap; m.list_len = 0;
-    m.counts = gcnt; m.count_stride = 0;           // query b holds gcnt[b] dense candidates
-    m.k = kc; m.tau = nullptr; m.out_s = c1s; m.out_i = c1i; m.out_stride = kc;
-    if (int rc = launch_merge(m, B, stream)) return rc;
+  // RESIDENT kernels on a large store run pass 2 as two ranges: a head of ~15 % of the tiles
+  // filtered against pass 1's threshold, tau_refine (the head's survivors are a 4x larger sample
+  // than pass 1's), then the rest against the tighter threshold -- the rare path of the epilogue
+  // fires ~3x less often overall (profiles/r02_k3_probe.txt).  Survivors of both ranges land in the
+  // same dense per-query lists; every row at or above the FINAL tau is among them.
+  int head_tiles = 0;
+  if (plan.mt > 0 && n_tiles >= 16384) head_tiles = (int)(0.15 * n_tiles);
+  if (const char* e = getenv("B200VS_GEMM_HEAD")) { if (*e) head_tiles = (int)(atof(e) * n_tiles); }   // diagnostic
+  if (head_tiles > 0 && head_tiles < n_tiles) {
+    p.n_tiles = head_tiles;
+    if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
+    tau_refine_kernel<<<(B + kTauWarps - 1) / kTauWarps, kTauWarps * 32, 0, stream>>>(gls, gcnt, ks, B, tau);
+    count_launch();
+    VS_CHECK_LAUNCH();
+    p.tile_first = head_tiles; p.n_tiles = n_tiles - head_tiles;
   }
-  // K5 + final K4 + certification, one CTA per query
+  if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
+  // candidate selection + K5 + final ordering + certification, one CTA per query
   {
     FinishParams f = {};
     f.q = q; f.dim = s->dim; f.ld = s->ld; f.metric = s->metric; f.B = B; f.k = kk; f.kc = kc; f.n_rows = n;
     f.rows = (const float*)s->rows.ptr(); f.norms = (const float*)s->norms.ptr(); f.id_map = s->id_map();
-    f.cand_s = c1s; f.cand_i = c1i; f.tau = tau; f.overflow = ovf; f.qerr = qerr; f.qlen = qlen;
-    f.bounds = s->bounds; f.slack = 4.f * (float)s->dim * 5.9604645e-8f + 1e-6f; f.certify = certify ? 1 : 0;
-    f.out_s = out_scores; f.out_i = out_ids; f.out_stride = out_stride; f.n_bad = nbad; f.bad_list = bad;
-    finish_kernel<<<B, kFinishThreads, (size_t)s->ld * 4, stream>>>(f);
+    f.glist_s = gls; f.glist_i = gli; f.gcount = gcnt;
+    f.tau = tau; f.overflow = ovf; f.qerr = qerr; f.qlen = qlen; f.bounds = s->bounds;
+    // fp32 accumulation error of the tensor core and of the exact kernels, relative to ||u|| ||v||
+    // (tests/test_gemm_gpu.py measures the tensor core's share against float64)
+    f.slack = (l2 ? 8.f : 4.f) * (float)s->dim * 5.9604645e-8f + 1e-6f;
+    f.certify = certify ? 1 : 0;
+    f.out_s = out_scores; f.out_i = out_ids; f.out_stride = out_stride; f.bad = bad;
+    const size_t smem = (size_t)kGlobalCap * 8 + (size_t)s->ld * 4;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(select_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    select_finish_kernel<<<B, kFinishThreads, smem, stream>>>(f);
     count_launch();
     VS_CHECK_LAUNCH();
   }
   if (!certify) return VS_OK;
-  int h_bad = 0;
-  VS_CUDA(cudaMemcpyAsync(&h_bad, nbad, 4, cudaMemcpyDeviceToHost, stream));
-  VS_CUDA(cudaStreamSynchronize(stream));
-  if (h_bad == 0) return VS_OK;
-  // second chance / exact fp32 scan for the queries that could not be certified
-  float* gq = nullptr; float* ts = nullptr; int32_t* ti = nullptr;
-  VS_CUDA(cudaMallocAsync((void**)&gq, (size_t)h_bad * s->dim * 4, stream));
-  VS_CUDA(cudaMallocAsync((void**)&ts, (size_t)h_bad * kk * 4, stream));
-  VS_CUDA(cudaMallocAsync((void**)&ti, (size_t)h_bad * kk * 4, stream));
-  gather_queries_kernel<<<std::min(1184, (h_bad * s->dim + 255) / 256), 256, 0, stream>>>(q, s->dim, bad, h_bad, gq);
-  count_launch();
-  int rc;
-  const int kc_retry = std::min(4 * kc, kMaxCand);
-  if (kc_want == 0 && kc_retry > kc && (int64_t)kc_retry * 8 <= n) {
-    s->retries.fetch_add(h_bad);
-    rc = gemm_block(s, n, gq, h_bad, kk, true, scan_tma, ts, ti, kk, kc_retry, false, stream);
-  } else {
-    s->fallbacks.fetch_add(h_bad);
-    rc = scan_queries_exact(s, n, gq, h_bad, kk, scan_tma, ts, ti, kk, stream);
-  }
-  if (!rc) {
-    scatter_results_kernel<<<std::min(1184, (h_bad * kk + 255) / 256), 256, 0, stream>>>(ts, ti, kk, bad, h_bad,
-                                                                                       out_scores, out_ids, out_stride);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) rc = cuda_fail(e, "scatter_results_kernel", __FILE__, __LINE__);
-  }
-  cudaFreeAsync(gq, stream);
-  cudaFreeAsync(ts, stream);
-  cudaFreeAsync(ti, stream);
-  return rc;
+  VS_CUDA(cudaMemcpyAsync(s->slots[slot].h_bad, bad, 4, cudaMemcpyDeviceToHost, stream));
+  VS_CUDA(cudaEventRecord(s->slots[slot].done, stream));
+  guard.keep = true;
+  pending->slot = slot; pending->q = q; pending->B = B; pending->kk = kk; pending->kc_want = kc_want;
+  pending->n = n; pending->scan_tma = scan_tma; pending->row_mask = row_mask;
+  pending->out_s = out_scores; pending->out_i = out_ids; pending->out_stride = out_stride;
+  return VS_OK;
 }
 
+// Wait for the block's certification count; re-run what could not be certified -- once through
+// K3 with 4x the candidates (a wider 16-bit margin), then through the exact fp32 scan -- and
+// scatter those results over the block's output rows.  The common case (count 0) only waits.
+static int gemm_block_complete(vs_store* s, const PendingBlock& pb, cudaStream_t stream) {
+  if (pb.slot < 0) return VS_OK;
+  vs_store::CertSlot& c = s->slots[pb.slot];
+  cudaError_t e = cudaEventSynchronize(c.done);
+  const int h_bad = *c.h_bad;
+  if (e != cudaSuccess) { release_slot(s, pb.slot); return cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__); }
+  if (h_bad == 0) { release_slot(s, pb.slot); return VS_OK; }
+  struct Bufs {
+    float* gq = nullptr; float* ts = nullptr; int32_t* ti = nullptr; cudaStream_t st;
+    ~Bufs() { if (gq) cudaFreeAsync(gq, st); if (ts) cudaFreeAsync(ts, st); if (ti) cudaFreeAsync(ti, st); }
+  } bufs;
+  bufs.st = stream;
+  struct Rel { vs_store* s; int slot; ~Rel() { release_slot(s, slot); } } rel{s, pb.slot};
+  const int kk = pb.kk;
+  const int32_t* bad = c.d_bad + 1;
+  VS_CUDA(cudaMallocAsync((void**)&bufs.gq, (size_t)h_bad * s->dim * 4, stream));
+  VS_CUDA(cudaMallocAsync((void**)&bufs.ts, (size_t)h_bad * kk * 4, stream));
+  VS_CUDA(cudaMallocAsync((void**)&bufs.ti, (size_t)h_bad * kk * 4, stream));
+  gather_queries_kernel<<<std::min(1184, (h_bad * s->dim + 255) / 256), 256, 0, stream>>>(pb.q, s->dim, bad, h_bad, bufs.gq);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  int rc;
+  const int kc = (int)std::min<int64_t>(cand_count(kk), pb.n);
+  const int kc_retry = std::min(4 * kc, kMaxCand);
+  if (pb.kc_want == 0 && kc_retry > kc && (int64_t)kc_retry * 8 <= pb.n) {
+    s->retries.fetch_add(h_bad);
+    PendingBlock again;
+    rc = gemm_block_enqueue(s, pb.n, bufs.gq, h_bad, kk, true, pb.scan_tma, pb.row_mask, pb.n, bufs.ts, bufs.ti, kk,
+                            kc_retry, false, stream, &again);
+    if (!rc) rc = gemm_block_complete(s, again, stream);
+  } else {
+    s->fallbacks.fetch_add(h_bad);
+    rc = scan_queries_exact(s, pb.n, bufs.gq, h_bad, kk, pb.scan_tma, pb.row_mask, bufs.ts, bufs.ti, kk, stream);
+  }
+  if (rc) return rc;
+  scatter_results_kernel<<<std::min(1184, (h_bad * kk + 255) / 256), 256, 0, stream>>>(bufs.ts, bufs.ti, kk, bad, h_bad,
+                                                                                     pb.out_s, pb.out_i, pb.out_stride);
+  count_launch();
+  VS_CHECK_LAUNCH();
+  return VS_OK;
+}
+
+// Enqueue the whole search (blocks of kMaxQueriesPerLaunch queries).  With `ticket` the
+// certification checks are left pending in it (gemm_complete finishes them); without, every
+// block is completed before the next one is enqueued.
 int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certify, bool scan_tma, bool fp8,
-              float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
+              const uint32_t* row_mask, int64_t n_live, float* out_scores, int32_t* out_ids, int64_t out_stride,
+              cudaStream_t stream, vs_ticket* ticket) {
   if (fp8) {
     if (!s->shadow8) { set_error("store was created without an fp8 shadow copy (VS_SHADOW_FP8)"); return VS_ERR_STATE; }
     certify = false;            // e4m3 rounding is far above any top-k margin: recall-reported variant
   } else if (!s->shadow) { set_error("store was created without a 16-bit shadow copy"); return VS_ERR_STATE; }
-  if (s->metric == VS_METRIC_EUCLIDEAN) { set_error("the GEMM path serves cosine and dot_product"); return VS_ERR_STATE; }
   if (cand_count(kk) > kMaxCand) { set_error("invalid argument: k too large for the GEMM path (k <= 128)"); return VS_ERR_INVALID; }
   // the fp8 variant keeps 4x the candidates for the exact rescoring
   const int kc_want = fp8 ? std::min(4 * cand_count(kk), kMaxCand) : 0;
   for (int b0 = 0; b0 < B; b0 += kMaxQueriesPerLaunch) {
     const int nb = std::min(kMaxQueriesPerLaunch, B - b0);
-    if (int rc = gemm_block(s, n, q + (size_t)b0 * s->dim, nb, kk, certify, scan_tma,
-                            out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride, out_stride,
-                            kc_want, fp8, stream))
+    PendingBlock pb;
+    if (int rc = gemm_block_enqueue(s, n, q + (size_t)b0 * s->dim, nb, kk, certify, scan_tma, row_mask, n_live,
+                                    out_scores + (int64_t)b0 * out_stride, out_ids + (int64_t)b0 * out_stride,
+                                    out_stride, kc_want, fp8, stream, &pb))
       return rc;
+    if (pb.slot < 0) continue;
+    if (ticket) ticket->blocks.push_back(pb);
+    else if (int rc = gemm_block_complete(s, pb, stream)) return rc;
   }
   return VS_OK;
+}
+
+int gemm_complete(vs_store* s, vs_ticket* ticket) {
+  int rc = VS_OK;
+  for (auto& pb : ticket->blocks) {
+    const int r = gemm_block_complete(s, pb, ticket->stream);
+    if (r && !rc) rc = r;
+  }
+  ticket->blocks.clear();
+  return rc;
 }
 
 // test / API helper: the full (B, n) bf16 tensor-core score matrix (kModeDump)
@@ -1264,7 +1500,7 @@ int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, 
   const int m_tiles = ((B + kTileM * cg - 1) / (kTileM * cg)) * cg;
   const int rows_padded = m_tiles * kTileM;
   GemmPlan plan;
-  plan_gemm(kch, m_tiles, cg, &plan);
+  plan_gemm(kch, m_tiles, cg, false, &plan);
   Ws ws;
   __nv_bfloat16* qb; float *qerr, *qlen;
   ws.want(&qb, (size_t)rows_padded * K);
@@ -1276,7 +1512,7 @@ int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, 
   if (int rc = make_map(&mq, qb, rows_padded, K, fp16 ? 1 : 0)) return rc;
   if (int rc = make_map(&mx, s->shadow_rows.ptr(), n, K, fp16 ? 1 : 0, x_box_rows(plan))) return rc;
   prep_queries_bf16_kernel<<<(rows_padded + 7) / 8, 256, 0, stream>>>(q, B, s->dim, s->metric, K, rows_padded, qb,
-                                                                    qerr, qlen);
+                                                                    qerr, qlen, nullptr, nullptr);
   count_launch();
   VS_CHECK_LAUNCH();
   GemmParams p = {};
@@ -1297,6 +1533,6 @@ extern "C" int vs_debug_gemm_scores(vs_store* s, const float* q, int B, float* o
   const int64_t n = s->count.load(std::memory_order_acquire);
   VS_REQUIRE(n > 0, "store is empty");
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (s->append_done && s->append_stream != stream) VS_CUDA(cudaStreamWaitEvent(stream, s->append_done, 0));
+  if (s->append_done && s->append_stream.load() != stream) VS_CUDA(cudaStreamWaitEvent(stream, s->append_done, 0));
   return gemm_dump_scores(s, n, q, B, out, n, stream);
 }

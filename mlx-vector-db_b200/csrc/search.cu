@@ -110,9 +110,9 @@ static int scan_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool
 }
 
 // exact fp32 scan of a query set (the GEMM path's fallback for uncertified queries)
-int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, float* out_scores,
-                       int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
-  return scan_path(s, n, q, B, kk, false, use_tma, nullptr, out_scores, out_ids, out_stride, true, stream);
+int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, const uint32_t* row_mask,
+                       float* out_scores, int32_t* out_ids, int64_t out_stride, cudaStream_t stream) {
+  return scan_path(s, n, q, B, kk, false, use_tma, row_mask, out_scores, out_ids, out_stride, true, stream);
 }
 
 // exact fp32 rescoring of (B, kc) candidate ids + final ordering into (B, out_stride)
@@ -139,16 +139,18 @@ using namespace vs;
 
 extern "C" {
 
-int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32_t* row_mask,
-              float* out_scores, int32_t* out_ids, void* stream_) {
+// Common body of vs_search / vs_search_submit.  ticket == NULL: certification checks are done
+// before returning (one host wait per GEMM block); otherwise they stay pending in the ticket.
+static int search_impl(vs_store* s, const float* q, int B, int k, int flags, const uint32_t* row_mask,
+                       int64_t mask_live, float* out_scores, int32_t* out_ids, cudaStream_t stream,
+                       vs_ticket* ticket) {
   VS_REQUIRE(s != nullptr, "store is NULL");
   VS_REQUIRE(B >= 0, "B must be >= 0");
   if (B == 0 || k <= 0) return VS_OK;
   VS_REQUIRE(q && out_scores && out_ids, "NULL pointer");
-  cudaStream_t stream = (cudaStream_t)stream_;
   VS_CUDA(cudaSetDevice(s->device));
   const int64_t n = s->count.load(std::memory_order_acquire);
-  if (s->append_done && s->append_stream != stream)
+  if (s->append_done && s->append_stream.load(std::memory_order_acquire) != stream)
     VS_CUDA(cudaStreamWaitEvent(stream, s->append_done, 0));
   if (n == 0) {
     const int64_t total = (int64_t)B * k;
@@ -163,9 +165,12 @@ int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32
   bool use_tma = default_tma();
   if (flags & VS_SEARCH_TMA) use_tma = true;
   if (flags & VS_SEARCH_LDG) use_tma = false;
+  // rows taking part: the mask's popcount when the caller knows it (the GEMM path sizes its
+  // sample from it; unknown -> the masked scan)
+  const int64_t n_live = row_mask == nullptr ? n : mask_live;
   if (mode == VS_SEARCH_AUTO) {
     mode = VS_SEARCH_SCAN_FP32;
-    if (gemm_supported(s, n, B, kk) && row_mask == nullptr) mode = VS_SEARCH_GEMM;
+    if (gemm_supported(s, n, B, kk) && (row_mask == nullptr || (n_live >= 0 && n_live * 5 >= n))) mode = VS_SEARCH_GEMM;
   }
   switch (mode) {
     case VS_SEARCH_SCAN_FP32:
@@ -186,15 +191,47 @@ int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32
     }
     case VS_SEARCH_GEMM:
     case VS_SEARCH_GEMM_NOCERT:
-      if (row_mask != nullptr) { set_error("row_mask is not supported by the GEMM path"); return VS_ERR_INVALID; }
-      return gemm_path(s, n, q, B, kk, mode == VS_SEARCH_GEMM, use_tma, false, out_scores, out_ids, k, stream);
     case VS_SEARCH_GEMM_FP8:
-      if (row_mask != nullptr) { set_error("row_mask is not supported by the GEMM path"); return VS_ERR_INVALID; }
-      return gemm_path(s, n, q, B, kk, false, use_tma, true, out_scores, out_ids, k, stream);
+      if (row_mask != nullptr && n_live < 0) {
+        set_error("invalid argument: the GEMM path needs mask_live (the number of set bits) with a row_mask");
+        return VS_ERR_INVALID;
+      }
+      return gemm_path(s, n, q, B, kk, mode == VS_SEARCH_GEMM, use_tma, mode == VS_SEARCH_GEMM_FP8, row_mask, n_live,
+                       out_scores, out_ids, k, stream, ticket);
     default:
       set_error("invalid argument: unknown search mode");
       return VS_ERR_INVALID;
   }
+}
+
+int vs_search(vs_store* s, const float* q, int B, int k, int flags, const uint32_t* row_mask, int64_t mask_live,
+              float* out_scores, int32_t* out_ids, void* stream_) {
+  return search_impl(s, q, B, k, flags, row_mask, mask_live, out_scores, out_ids, (cudaStream_t)stream_, nullptr);
+}
+
+int vs_search_submit(vs_store* s, const float* q, int B, int k, int flags, const uint32_t* row_mask,
+                     int64_t mask_live, float* out_scores, int32_t* out_ids, void* stream_, vs_ticket** ticket_out) {
+  VS_REQUIRE(ticket_out != nullptr, "ticket_out is NULL");
+  *ticket_out = nullptr;
+  vs_ticket* t = new vs_ticket();
+  t->stream = (cudaStream_t)stream_;
+  const int rc = search_impl(s, q, B, k, flags, row_mask, mask_live, out_scores, out_ids, t->stream, t);
+  if (rc) {                      // blocks already enqueued still hold slots: finish them, keep the first error
+    gemm_complete(s, t);
+    delete t;
+    return rc;
+  }
+  *ticket_out = t;
+  return VS_OK;
+}
+
+int vs_search_complete(vs_store* s, vs_ticket* ticket) {
+  VS_REQUIRE(s != nullptr, "store is NULL");
+  if (ticket == nullptr) return VS_OK;
+  VS_CUDA(cudaSetDevice(s->device));
+  const int rc = gemm_complete(s, ticket);
+  delete ticket;
+  return rc;
 }
 
 int vs_rescore(vs_store* s, const float* q, int B, const int32_t* cand_ids, int kc, int k,
@@ -210,7 +247,7 @@ int vs_rescore(vs_store* s, const float* q, int B, const int32_t* cand_ids, int 
 }
 
 int vs_search_host(vs_store* s, const float* q_host, int B, int k, int flags,
-                   const uint32_t* row_mask_dev, float* out_scores_host, int32_t* out_ids_host) {
+                   const uint32_t* row_mask_dev, int64_t mask_live, float* out_scores_host, int32_t* out_ids_host) {
   VS_REQUIRE(s != nullptr, "store is NULL");
   VS_REQUIRE(B >= 0, "B must be >= 0");
   if (B == 0 || k <= 0) return VS_OK;
@@ -233,7 +270,7 @@ int vs_search_host(vs_store* s, const float* q_host, int B, int k, int flags,
   } else {
     VS_CUDA(cudaMemcpyAsync(dq, q_host, qbytes, cudaMemcpyHostToDevice, stream));
   }
-  if (int rc = vs_search(s, dq, B, k, flags, row_mask_dev, ds, di, stream)) return rc;
+  if (int rc = vs_search(s, dq, B, k, flags, row_mask_dev, mask_live, ds, di, stream)) return rc;
   if (staged) {
     unsigned char* po = (unsigned char*)s->pinned_out;
     VS_CUDA(cudaMemcpyAsync(po, ds, obytes, cudaMemcpyDeviceToHost, stream));

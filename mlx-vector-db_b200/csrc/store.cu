@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 #include "store.cuh"
+#include "gemm_topk.cuh"
 
 namespace vs {
 
@@ -512,6 +513,7 @@ int vs_destroy(vs_store* s) {
   s->shadow_rows.destroy();
   s->shadow8_rows.destroy();
   s->gids.destroy();
+  free_cert_slots(s);
   if (s->bounds) cudaFree(s->bounds);
   if (s->append_done) cudaEventDestroy(s->append_done);
   if (s->host_stream) cudaStreamDestroy(s->host_stream);
@@ -635,7 +637,7 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
   if (!rows_on_device) VS_CUDA(cudaStreamSynchronize(stream));  // host buffer may be reused
   // searches on other streams wait for this event before reading the new rows
   VS_CUDA(cudaEventRecord(s->append_done, stream));
-  s->append_stream = stream;
+  s->append_stream.store(stream, std::memory_order_release);
   if (with_ids) s->mapped = true;
   s->count.store(n1, std::memory_order_release);
   return VS_OK;
@@ -660,6 +662,9 @@ int vs_read_rows(vs_store* s, int64_t first, int64_t m, float* out, int out_on_d
   VS_REQUIRE(out != nullptr, "out is NULL");
   cudaStream_t stream = (cudaStream_t)stream_;
   VS_CUDA(cudaSetDevice(s->device));
+  // rows appended on another stream: wait for their K1 (the copy below must not overtake it)
+  if (s->append_done && s->append_stream.load(std::memory_order_acquire) != stream)
+    VS_CUDA(cudaStreamWaitEvent(stream, s->append_done, 0));
   const float* src = (const float*)s->rows.ptr() + first * s->ld;
   VS_CUDA(cudaMemcpy2DAsync(out, (size_t)s->dim * 4, src, (size_t)s->ld * 4, (size_t)s->dim * 4,
                             (size_t)m, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,

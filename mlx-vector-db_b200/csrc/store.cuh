@@ -1,6 +1,7 @@
 // Host-side state of one store: growable HBM arenas + row count.
 #pragma once
 #include <cuda.h>
+#include <deque>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -47,7 +48,11 @@ struct vs_store {
   std::atomic<int64_t> retries{0};     // queries retried with 4x the candidates first
   std::mutex mu;                 // one writer at a time (append / reset)
   cudaEvent_t append_done = nullptr;   // recorded after the last append's kernels
-  cudaStream_t append_stream = nullptr;
+  std::atomic<cudaStream_t> append_stream{nullptr};   // read by concurrent searches
+  // certification slots of the GEMM path (gemm_topk.cu): pinned count + event + device list
+  struct CertSlot { cudaEvent_t done = nullptr; int* h_bad = nullptr; int32_t* d_bad = nullptr; bool busy = false; };
+  std::mutex slot_mu;
+  std::deque<CertSlot> slots;    // deque: growing never moves a slot another thread is using
   // vs_search_host: private stream + pinned staging, serialised by host_mu
   std::mutex host_mu;
   cudaStream_t host_stream = nullptr;

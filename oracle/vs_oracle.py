@@ -335,13 +335,14 @@ class OracleVectorStore:
 # --------------------------------------------------------------------------- #
 # timed variant for bench.py's CPU baseline / reference arm
 # --------------------------------------------------------------------------- #
-def batch_similarity_search_timed(queries, db, k: int = 10, threads: int = 1):
+def batch_similarity_search_timed(queries, db, k: int = 10, threads: int = 1, return_scores: bool = False):
     """`batch_similarity_search` (performance/mlx_optimized.py:217-248) with its three phases
     timed separately and spread over `threads` host threads where NumPy itself is serial:
     (1) normalise queries and the WHOLE database (:69-83, done on every call by the
     reference), (2) one fp32 GEMM (:86, BLAS threads), (3) per-row full stable argsort of the
     negated scores + gather (:235-244).  Same arithmetic and tie rule as the untimed function.
-    Returns (ids, scores, {"normalize_s", "matmul_s", "argsort_s"})."""
+    Returns (ids, scores, {"normalize_s", "matmul_s", "argsort_s"}); with `return_scores` the
+    dict also carries the full (B, N) score matrix under "score_matrix" (for compare_topk)."""
     import time
     from concurrent.futures import ThreadPoolExecutor
 
@@ -378,4 +379,41 @@ def batch_similarity_search_timed(queries, db, k: int = 10, threads: int = 1):
 
         list(ex.map(_sort_row, range(B)))
         t3 = time.perf_counter()
-    return ids, sc, {"normalize_s": t1 - t0, "matmul_s": t2 - t1, "argsort_s": t3 - t2}
+    t = {"normalize_s": t1 - t0, "matmul_s": t2 - t1, "argsort_s": t3 - t2}
+    if return_scores:
+        t["score_matrix"] = s
+    return ids, sc, t
+
+
+def batch_similarity_search_optimized_timed(queries, db_normalized, k: int = 10, threads: int = 1):
+    """The "optimised CPU" line of BASELINE.md section 2: what a careful CPU implementation of the
+    same search would do -- database normalised ONCE (passed in, untimed), one fp32 GEMM, then
+    `argpartition` to the best k and a sort of those k instead of a full sort of N.  Same results
+    as `batch_similarity_search` up to the tie order inside the k-th score.  Separates the
+    reference's algorithmic waste (per-call re-normalisation, full argsort) from the hardware.
+    Returns (ids, scores, {"matmul_s", "select_s"})."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    q = to_f32(queries)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    B, n = q.shape[0], db_normalized.shape[0]
+    kk = max(0, min(int(k), n))
+    t0 = time.perf_counter()
+    qn = q / np.maximum(_row_norms(q), EPS)
+    s = qn @ db_normalized.T
+    t1 = time.perf_counter()
+    ids = np.empty((B, kk), np.int32)
+    sc = np.empty((B, kk), np.float32)
+
+    def _select_row(b):
+        part = np.argpartition(-s[b], kk - 1)[:kk] if kk < n else np.arange(n)
+        order = part[np.lexsort((part, -s[b][part]))]
+        ids[b] = order
+        sc[b] = s[b][order]
+
+    with ThreadPoolExecutor(max_workers=max(1, int(threads))) as ex:
+        list(ex.map(_select_row, range(B)))
+    t2 = time.perf_counter()
+    return ids, sc, {"matmul_s": t1 - t0, "select_s": t2 - t1}

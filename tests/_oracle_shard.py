@@ -29,16 +29,42 @@ class OracleShard:
     def new_pack(self, B, k):
         return torch.empty((2, B, k), dtype=torch.int32)
 
-    def search_into(self, q, k, pack):
+    def search_into(self, q, k, pack, row_mask=None):
         B = q.shape[0]
         ids = np.full((B, k), -1, np.int32)
         sc = np.zeros((B, k), np.float32)
-        if self.rows.shape[0]:
-            li, ls, _ = vs_oracle.search(q.numpy(), self.rows, k, self.metric)
-            ids[:, :li.shape[1]] = self.gids[li]
+        rows, gids = self.rows, self.gids
+        if row_mask is not None:          # the reference gathers the filtered rows (:167)
+            rows, gids = rows[row_mask], gids[row_mask]
+        if rows.shape[0]:
+            li, ls, _ = vs_oracle.search(q.numpy(), rows, k, self.metric)
+            ids[:, :li.shape[1]] = gids[li]
             sc[:, :li.shape[1]] = ls
         pack[0].copy_(torch.from_numpy(sc.view(np.int32)))
         pack[1].copy_(torch.from_numpy(ids))
+
+    def submit_into(self, q, k, pack, row_mask=None, mask_live=-1):
+        self.search_into(q, k, pack, row_mask)
+        return None
+
+    def make_row_mask(self, hit):
+        return np.asarray(hit, dtype=np.bool_).copy()
+
+    def reset(self):
+        self.rows = np.zeros((0, self.dimension), np.float32)
+        self.gids = np.zeros((0,), np.int32)
+
+    def memory_bytes(self):
+        return int(self.rows.nbytes)
+
+    def read_rows(self, first, m):
+        return self.rows[first:first + m].copy()
+
+    def complete(self, ticket):
+        pass
+
+    def last_complete_enqueued_work(self):
+        return False
 
     def merge(self, gathered, G, B, k):
         g = gathered.numpy()

@@ -43,7 +43,7 @@ def test_argument_validation_needs_no_gpu(native_lib):
     with pytest.raises(ValueError):
         _cabi.check(native_lib.vs_create(0, 8, 7, 0, 0, C.byref(h)))          # bad metric
     with pytest.raises(ValueError):
-        _cabi.check(native_lib.vs_search(None, None, 1, 1, 0, None, None, None, None))
+        _cabi.check(native_lib.vs_search(None, None, 1, 1, 0, None, -1, None, None, None))
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

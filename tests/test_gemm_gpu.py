@@ -223,3 +223,97 @@ def test_gemm_modes_on_a_small_store_use_the_exact_scan(make_store):
         ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES[mode])
         rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
         assert rep.ok, (mode, f"{rep}")
+
+
+L2_SHAPES = [
+    # N, D, B, k
+    (70000, 128, 64, 10),      # resident kernel, ||x||^2 staged per tile
+    (70001, 128, 300, 10),     # ragged last tile: rows past the end must score -inf
+    (66000, 384, 130, 10),     # streaming kernel (CTA pairs, 256-row tiles)
+    (80000, 256, 40, 100),     # top-100 (config C's k)
+    (66000, 1536, 16, 100),    # config C's shape, smaller N
+]
+
+
+@pytest.mark.parametrize("shape", L2_SHAPES, ids=[f"N{n}_D{d}_B{b}_k{k}" for n, d, b, k in L2_SHAPES])
+@pytest.mark.parametrize("dist", ["normal", "uniform"])
+def test_euclidean_gemm_search_matches_oracle(make_store, shape, dist):
+    """K3 for euclidean: candidate key 2 q^.x^ - ||x||^2 over the bf16 shadow, direct-difference
+    fp32 rescoring, certification in squared-distance space (service/optimized_vector_store.py:43-48)."""
+    from b200vs import _cabi
+    n, d, B, k = shape
+    db = datasets.make_db(n, d, dist)
+    q = datasets.make_queries(B, d, dist)
+    st = make_store(d, "euclidean")
+    st.add_vectors(db, [])
+    ref_ids, ref_scores, S = vs_oracle.search(q, db, k, "euclidean")
+    ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["gemm"])
+    rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, S)
+    assert rep.ok, f"{rep}"
+    ids2, scores2 = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES["scan_fp32"])
+    np.testing.assert_array_equal(ids, ids2)
+    np.testing.assert_array_equal(scores, scores2)
+    fb = int(_cabi.lib().vs_fallback_count(st._handle))
+    assert fb <= B // 4, f"{fb} of {B} queries fell back to the exact scan"
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+@pytest.mark.parametrize("keep", [0.5, 0.25])
+def test_masked_gemm_search_matches_oracle_on_the_subset(make_store, metric, keep):
+    """Metadata filter pushed into K3 (service/optimized_vector_store.py:159-167): the row bitmap is
+    applied in the epilogue; results equal the oracle's search over the filtered rows."""
+    from b200vs import _cabi
+    n, d, B, k = 90000, 128, 48, 10
+    db = datasets.make_db(n, d)
+    q = datasets.make_queries(B, d)
+    rng = np.random.default_rng(7)
+    hit = rng.random(n) < keep
+    st = make_store(d, metric)
+    st.add_vectors(db, [])
+    bits = np.packbits(hit, bitorder="little")
+    buf = np.zeros(((n + 31) // 32 + 1) * 4, np.uint8)
+    buf[:bits.size] = bits
+    mask = torch.from_numpy(buf.view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    sub = np.nonzero(hit)[0]
+    ref_ids, ref_scores, S = vs_oracle.search(q, db[sub], k, metric)
+    ref_ids = sub[ref_ids].astype(np.int32)
+    Sfull = np.full((B, n), -np.inf if metric == "cosine" else np.inf, np.float32)
+    Sfull[:, sub] = S
+    for mode in ("gemm", "scan_fp32", "auto"):
+        ids, scores = st.search_arrays(q, k, flags=_cabi.SEARCH_MODES[mode], row_mask=mask, mask_live=int(hit.sum()))
+        rep = compare.compare_topk(ref_ids, ref_scores, ids, scores, Sfull)
+        assert rep.ok, f"{mode}: {rep}"
+        assert hit[ids].all(), f"{mode}: a masked row was returned"
+
+
+def test_submit_complete_keeps_batches_in_flight(make_store):
+    """vs_search_submit / vs_search_complete: three searches enqueued back to back, completed
+    afterwards, equal the synchronous vs_search results."""
+    from b200vs import _cabi
+    lib = _cabi.lib()
+    n, d, B, k = 70000, 128, 64, 10
+    db = datasets.make_db(n, d)
+    st = make_store(d, "cosine")
+    st.add_vectors(db, [])
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    qs = [torch.from_numpy(datasets.make_queries(B, d, seed=100 + i)).cuda() for i in range(3)]
+    outs, tickets = [], []
+    for qd in qs:
+        s_ = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        i_ = torch.empty((B, k), dtype=torch.int32, device="cuda")
+        t = C.c_void_p()
+        _cabi.check(lib.vs_search_submit(st._handle, C.c_void_p(qd.data_ptr()), B, k, _cabi.SEARCH_GEMM, None, -1,
+                                         C.c_void_p(s_.data_ptr()), C.c_void_p(i_.data_ptr()), stream, C.byref(t)))
+        outs.append((s_, i_))
+        tickets.append(t)
+    for t in tickets:
+        _cabi.check(lib.vs_search_complete(st._handle, t))
+    torch.cuda.synchronize()
+    for qd, (s_, i_) in zip(qs, outs):
+        s2 = torch.empty_like(s_)
+        i2 = torch.empty_like(i_)
+        _cabi.check(lib.vs_search(st._handle, C.c_void_p(qd.data_ptr()), B, k, _cabi.SEARCH_SCAN_FP32, None, -1,
+                                  C.c_void_p(s2.data_ptr()), C.c_void_p(i2.data_ptr()), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(i_, i2) and torch.equal(s_, s2)

@@ -38,6 +38,13 @@ WORKLOADS = {          # name -> (rows, dim)
 N_BLOCKS = 8           # the database is generated in 8 seeded blocks so every N in {1,2,4,8} sees the same rows
 DB_SEED, QUERY_SEED = 1234, 4321
 METRIC_NAME = "queries/sec exact top-10 cosine"
+_T0 = time.perf_counter()
+
+
+def log(msg: str) -> None:
+    """Progress to stderr (stdout carries the ONE JSON line): phase + seconds since start."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def parse_args():
@@ -621,6 +628,27 @@ def run_b200(args):
                 clocks["sampled"] = f"under the same load right after the timed region ({extra} extra steps)"
         scan_ms, scan_n = read_profile(0)
         gemm_ms, gemm_n = read_profile(1)
+        prof_steps, prof_note = steps, "CUDA events around every launch of the kernel, on its launch stream, over the timed region"
+        if getattr(st, "overlap_streams", False):
+            # two searches were in flight on two streams: an event bracket around a kernel then also holds
+            # the time it queued behind the other search's kernels.  The kernel's own duration is taken
+            # from a serial pass (one stream, one search at a time) of the same step right after.
+            st.overlap_streams = False
+            prof_steps = max(3, min(steps, 10))
+            st.search(q_dev, k)
+            barrier()
+            lib.vs_profile(1)
+            read_profile(0), read_profile(1)
+            for _ in range(prof_steps):
+                st.search(q_dev, k)
+            barrier()
+            lib.vs_profile(0)
+            scan_ms, scan_n = read_profile(0)
+            gemm_ms, gemm_n = read_profile(1)
+            st.overlap_streams = True
+            prof_note = (f"CUDA events around every launch of the kernel in a SERIAL pass of {prof_steps} steps right after the "
+                         "timed region (the timed region keeps two searches in flight on two streams, where a per-kernel "
+                         "bracket would include queueing behind the other search)")
         res = {"ms_per_step": ms / steps, "qps": B * steps / (ms / 1e3), "launches": int(launches),
                "exact_fallback_queries_per_step": (int(lib.vs_fallback_count(st.shard.handle)) - fb0) /
                                                   max(1, warmup + steps + (extra if ms < 700.0 else 0)),
@@ -634,7 +662,7 @@ def run_b200(args):
             # duration of the step's GEMM launches; the slower of the two rooflines bounds it
             flops = 2.0 * B * n_local * d
             bytes16 = float(n_local) * d * 2
-            per_step = gemm_ms / steps
+            per_step = gemm_ms / prof_steps
             peak = tc_sust if ms > 1000 else tc_burst
             kname = ("gemm_topk (K3: tcgen05 kind::f16, fp16 operands for cosine / bf16 for dot and "
                      "euclidean, fp32 accumulators in TMEM; pass 1 sample + pass 2 filter)")
@@ -644,9 +672,10 @@ def run_b200(args):
                                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                                    "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16 cuBLAS "
                                                   f"({'sustained' if ms > 1000 else 'burst'})",
-                                   "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
-                                   "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
-                                   "scan_fallback_ms_per_step": scan_ms / steps,
+                                   "launches": int(gemm_n), "launches_per_step": gemm_n / prof_steps,
+                                   "kernel_ms_per_step": per_step, "kernel_share_of_step": per_step / (ms / steps),
+                                   "kernel_timing": prof_note,
+                                   "scan_fallback_ms_per_step": scan_ms / prof_steps,
                                    # the runs are power-capped (clocks.reasons): the sustained cuBLAS figure
                                    "frac_of_sustained_peak": ach / tc_sust, "sustained_peak": tc_sust,
                                    "hbm_gbs_of_16bit_rows": bytes16 / (per_step * 1e-3) / 1e9}
@@ -658,9 +687,10 @@ def run_b200(args):
                                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                                    "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
                                    "algorithmic_bytes": "N_local * D * 2 (one pass over the 16-bit shadow rows)",
-                                   "launches": int(gemm_n), "launches_per_step": gemm_n / steps,
-                                   "kernel_ms_per_step": per_step, "kernel_share_of_step": gemm_ms / ms,
-                                   "scan_fallback_ms_per_step": scan_ms / steps,
+                                   "launches": int(gemm_n), "launches_per_step": gemm_n / prof_steps,
+                                   "kernel_ms_per_step": per_step, "kernel_share_of_step": per_step / (ms / steps),
+                                   "kernel_timing": prof_note,
+                                   "scan_fallback_ms_per_step": scan_ms / prof_steps,
                                    # north_star's roofline for the fp32 path: fp32 database bytes / HBM peak
                                    "fp32_scan_roofline_qps": B / (float(n_local) * d * 4 / (hbm_peak * 1e9)),
                                    "qps_vs_fp32_scan_roofline": (B * steps / (ms / 1e3)) /
@@ -672,8 +702,8 @@ def run_b200(args):
             res["roofline"] = {"kernel": "scan_topk (K2, fp32)", "bound": "hbm", "achieved": ach,
                                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                                "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
-                               "launches": int(scan_n), "avg_launch_ms": per,
-                               "kernel_share_of_step": scan_ms / ms}
+                               "launches": int(scan_n), "avg_launch_ms": per, "kernel_timing": prof_note,
+                               "kernel_share_of_step": (scan_ms / prof_steps) / (ms / steps)}
         if world == 1 and "roofline" in res:
             tp = ROOT / "profiles" / "traffic_r02.json"
             if tp.exists():
@@ -716,8 +746,11 @@ def run_b200(args):
 
     n, d = WORKLOADS[args.workload]
     B, k = args.batch, args.k
+    log(f"building the {args.workload} store ({n // world} rows per rank)")
     st = build_store(n, d, args.mode)
+    log(f"headline: batch {B}, {args.steps} steps")
     main = measure(st, n, d, B, k, args.steps, args.warmup, wl_name=args.workload)
+    log(f"headline done: {main['qps']:.0f} QPS, {main['ms_per_step']:.3f} ms/step")
 
     # cheap end-of-run sanity (not parity -- tests/ do that): rank-1 score bound, sortedness
     ids_h = main["ids"].cpu().numpy()
@@ -734,37 +767,57 @@ def run_b200(args):
 
     extras = []
     do_extras = args.extras if args.extras >= 0 else (1 if world == 1 else 0)
+    # The extras are context next to the headline: they run inside a time budget (seconds since
+    # start; the CPU leg behind them needs ~90 s) and whatever does not fit is listed as skipped,
+    # so the default run always ends within a few minutes.
+    budget = float(os.environ.get("B200VS_BENCH_BUDGET_S", "330"))
+
+    def within_budget(name):
+        if time.perf_counter() - _T0 < budget:
+            log(f"extra: {name}")
+            return True
+        log(f"extra skipped (time budget): {name}")
+        extras.append({"workload": name, "skipped": f"time budget of {budget:.0f} s reached"})
+        return False
+
     # batch 1 on the same sharded store at every N (north_star's 8-GPU target covers batch 1 too)
+    log("batch 1 (AUTO)")
     r = measure(st, n, d, 1, k, max(50, args.steps), args.warmup, wl_name=args.workload)
     extras.append(entry(f"{args.workload} batch 1 (AUTO: 16-bit tensor-core prefilter + certified fp32 rescoring)", r))
     if do_extras:
         short = max(3, min(args.steps, 10))
-        st.shard.flags = _cabi.SEARCH_MODES["scan_fp32"]
-        r = measure(st, n, d, 1, k, max(20, args.steps), args.warmup, wl_name=args.workload)
-        extras.append(entry(f"{args.workload} batch 1 via the fp32 scan (K2, mode scan_fp32)", r))
-        st.shard.flags = _cabi.SEARCH_MODES[args.mode]
-        r = measure(st, n, d, 32, k, max(20, args.steps), args.warmup)
-        extras.append(entry(f"{args.workload} batch 32", r))
+        if within_budget(f"{args.workload} batch 1 via the fp32 scan (K2, mode scan_fp32)"):
+            st.shard.flags = _cabi.SEARCH_MODES["scan_fp32"]
+            r = measure(st, n, d, 1, k, max(20, args.steps), args.warmup, wl_name=args.workload)
+            extras.append(entry(f"{args.workload} batch 1 via the fp32 scan (K2, mode scan_fp32)", r))
+            st.shard.flags = _cabi.SEARCH_MODES[args.mode]
+        if within_budget(f"{args.workload} batch 32"):
+            r = measure(st, n, d, 32, k, max(20, args.steps), args.warmup)
+            extras.append(entry(f"{args.workload} batch 32", r))
         st.close()
         del st
         torch.cuda.empty_cache()
         for name, batches in (("1Mx1536", (1, 1024)), ("1Mx768", (1, 1024))):
+            if not within_budget(f"{name} batches {batches}"):
+                continue
             n2, d2 = WORKLOADS[name]
             st2 = build_store(n2, d2, args.mode)
             for b2 in batches:
+                log(f"  {name} batch {b2}")
                 r = measure(st2, n2, d2, b2, k, max(20, args.steps) if b2 == 1 else short, args.warmup, wl_name=name)
                 extras.append(entry(f"{name} batch {b2}", r))
             if name == "1Mx1536":
+                log(f"  {name} batch 1 scan_fp32")
                 st2.shard.flags = _cabi.SEARCH_MODES["scan_fp32"]
                 r = measure(st2, n2, d2, 1, k, max(20, args.steps), args.warmup, wl_name=name)
                 extras.append(entry(f"{name} batch 1 via the fp32 scan (K2, mode scan_fp32)", r))
             st2.close()
             del st2
             torch.cuda.empty_cache()
-        extras.append(config_c_l2_bf16(dev, lib, _cabi, ShardedVectorStore, args))
-        extras.append(config_e_streaming(dev, lib, _cabi, ShardedVectorStore, args))
-        extras.append(k1_append_throughput(dev, lib, _cabi, ShardedVectorStore, args))
-        extras.append(fp8_variant(dev, lib, _cabi, ShardedVectorStore, args))
+        for name, fn in (("config C (1Mx1536 L2 top-100)", config_c_l2_bf16), ("config E (5Mx384 streaming)", config_e_streaming),
+                         ("K1 append throughput", k1_append_throughput), ("fp8 variant", fp8_variant)):
+            if within_budget(name):
+                extras.append(fn(dev, lib, _cabi, ShardedVectorStore, args))
     else:
         st.close()
 
@@ -775,14 +828,28 @@ def run_b200(args):
     if rank == 0 and (args.verify or (world == 1 and args.cpu_baseline)):
         threads = host_cores()
         limiter = set_host_threads(threads)
-        db_np, q_np = make_host_data(n, d, B)
+        log(f"CPU leg: generating the host copy of the database ({threads} threads)")
+        # the host copy holds the SAME rows and queries the engine searched: every block is
+        # regenerated on this rank's GPU from its seed (torch's CUDA generator, as build_store does)
+        # and copied to the host; the queries come from torch's CPU generator as in measure()
+        db_np = np.empty((n, d), np.float32)
+        per_block = n // N_BLOCKS
+        for b in range(N_BLOCKS):
+            g = torch.Generator(device=dev).manual_seed(DB_SEED + b)
+            gen = torch.rand if args.dist == "uniform" else torch.randn
+            blk = gen((per_block, d), generator=g, device=dev, dtype=torch.float32)
+            db_np[b * per_block:(b + 1) * per_block] = blk.cpu().numpy()
+            del blk
+        gq = torch.Generator().manual_seed(QUERY_SEED)
+        q_np = (torch.rand if args.dist == "uniform" else torch.randn)((B, d), generator=gq, dtype=torch.float32).numpy()
+        torch.cuda.empty_cache()
         sample_q = cpu_sample_queries(threads, B)
-        if args.dist != "normal":
-            args.verify = 0            # the host copy is generated for N(0,1) data only
+        log(f"CPU leg: oracle over the full database for {sample_q} queries")
         t, ref_ids, ref_sc = reference_step(db_np, q_np, k, sample_q, threads, return_scores=bool(args.verify))
         if args.verify:
             verified = verify_against_oracle(ref_ids, ref_sc, t.pop("score_matrix"), ids_h, sc_h)
         if world == 1 and args.cpu_baseline:
+            log("CPU leg: timed sample + optimised-CPU line")
             t, _, _ = reference_step(db_np, q_np, k, sample_q, threads)        # second sample: warm caches
             cpu_baseline = {
                 "value": extrapolate_qps(t, sample_q, B), "unit": "queries/s", "cores": threads, "kind": "port",
@@ -832,6 +899,12 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # watchdog: a bench that stops making progress dumps every thread's Python stack to stderr
+    # (B200VS_BENCH_WATCHDOG seconds between dumps; 0 = off)
+    wd = float(os.environ.get("B200VS_BENCH_WATCHDOG", "240") or 0)
+    if wd > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, repeat=True, file=sys.stderr)
     if args.impl == "reference":
         run_reference(args)
     else:

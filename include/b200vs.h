@@ -180,6 +180,22 @@ VS_API int vs_merge(int device, int metric, const float* cand_scores, const int3
                     int G, int B, int k, int64_t group_stride, float* out_scores,
                     int32_t* out_ids, void* stream);
 
+/* Candidate exchange over NVLink peer memory -- new (the reference is single-device): the
+ * fused replacement of "all-gather the per-GPU (B, k) results, then merge".  Every rank owns an
+ * exchange buffer all ranks of the box have mapped (the host side gets the peer pointers from
+ * torch.distributed's symmetric-memory rendezvous).
+ *   vs_exchange_push  copies `bytes` (a multiple of 16) from `src` (device) to peer_dst[g] for
+ *                     every rank g with direct stores over NVLink, then stores `step` with release
+ *                     semantics into peer_flag[g] (this rank's flag word in rank g's buffer).
+ *                     peer_dst / peer_flag are HOST arrays of G device pointers; `counter` is a
+ *                     zero-initialised device uint32 owned by the caller (block-completion count).
+ *   vs_exchange_wait  enqueues a one-warp kernel that returns once the G flag words at `flags`
+ *                     (this rank's own memory) are all >= step (traps after ~10 s: a dead rank
+ *                     must fail loudly).  vs_merge over the local buffer follows on the same stream. */
+VS_API int vs_exchange_push(int device, const void* src, int64_t bytes, void* const* peer_dst,
+                            void* const* peer_flag, int G, uint32_t step, void* counter, void* stream);
+VS_API int vs_exchange_wait(int device, const void* flags, int G, uint32_t step, void* stream);
+
 /* K5 rescore_fp32 -- exact fp32 scores (same arithmetic as the fp32 scan) for `kc`
  * candidate ids per query, sorted, best `k` written out.  cand_ids: (B, kc) device. */
 VS_API int vs_rescore(vs_store* s, const float* q, int B, const int32_t* cand_ids, int kc,

@@ -15,6 +15,7 @@ Differences from the reference, both deliberate:
 """
 from __future__ import annotations
 
+import re
 import threading
 import time
 from pathlib import Path
@@ -67,22 +68,46 @@ def _format(metric: str, raw_score: float, meta: Dict, rank: int) -> Dict[str, A
     return {"metadata": meta, "similarity_score": float(similarity), "distance": float(distance), "rank": rank}
 
 
-class StoreManager:
-    """api/routes/vectors.py:37-144: one store per `user_model` key, created on first use."""
+_ID_RE = re.compile(r"^[A-Za-z0-9][A-Za-z0-9.-]{0,63}$")
 
-    def __init__(self, base_path: str, dimension: int, metric: str, **config):
-        self.base = Path(base_path).expanduser()
+
+def _check_id(name: str, value: str) -> str:
+    """The reference guards these routes with API keys (out of scope here); this shim at least never
+    lets a request string leave `base_path`: ids are one path component of [A-Za-z0-9.-], no `_`
+    (so the `user_model` key below is unambiguous), no `..`."""
+    if not isinstance(value, str) or not _ID_RE.match(value) or ".." in value:
+        raise HTTPException(status_code=400, detail=f"invalid {name}")
+    return value
+
+
+class StoreManager:
+    """api/routes/vectors.py:37-144: one store per `user_model` key under
+    `<base>/<user_id>/<model_id>` (:57), created on first ADD; at most `max_stores` live stores."""
+
+    def __init__(self, base_path: str, dimension: int, metric: str, max_stores: int = 64, **config):
+        self.base = Path(base_path).expanduser().resolve()
         self.dimension, self.metric, self.config = dimension, metric, config
+        self.max_stores = max_stores
         self.stores: Dict[str, MLXVectorStore] = {}
         self.lock = threading.Lock()
 
-    def get(self, user_id: str, model_id: str) -> MLXVectorStore:
+    def get(self, user_id: str, model_id: str, create: bool = False) -> MLXVectorStore:
+        """The store of (user, model).  create=False (queries, counts): an id pair nobody has added
+        vectors for is a 404, not a new GPU handle -- unless a store of that name is on disk."""
+        user_id, model_id = _check_id("user_id", user_id), _check_id("model_id", model_id)
         key = f"{user_id}_{model_id}"
+        path = (self.base / user_id / model_id).resolve()
+        if self.base not in path.parents:
+            raise HTTPException(status_code=400, detail="invalid store path")
         with self.lock:
             st = self.stores.get(key)
             if st is None:
+                if not create and not path.exists():
+                    raise HTTPException(status_code=404, detail=f"Store not found: {user_id}/{model_id}")
+                if len(self.stores) >= self.max_stores:
+                    raise HTTPException(status_code=503, detail="too many open stores")
                 cfg = MLXVectorStoreConfig(dimension=self.dimension, metric=self.metric, **self.config)
-                st = self.stores[key] = MLXVectorStore(str(self.base / key), cfg)
+                st = self.stores[key] = MLXVectorStore(str(path), cfg)
             return st
 
     def close(self):
@@ -104,9 +129,11 @@ def create_app(base_path: str, dimension: int = 384, metric: str = "cosine", **c
         if not request.vectors or not request.metadata:
             raise HTTPException(status_code=400, detail="Vectors and metadata required")
         try:
-            store = manager.get(request.user_id, request.model_id)
+            store = manager.get(request.user_id, request.model_id, create=True)
             store.add_vectors(np.asarray(request.vectors, dtype=np.float32), request.metadata)
-        except Exception as e:           # the reference maps everything to 500 (:205-207)
+        except HTTPException:
+            raise
+        except Exception as e:           # the reference maps everything else to 500 (:205-207)
             raise HTTPException(status_code=500, detail=f"Failed to add vectors: {e}")
         return {"success": True, "vectors_added": len(request.vectors),
                 "total_vectors": store.get_stats()["vector_count"],
@@ -120,6 +147,8 @@ def create_app(base_path: str, dimension: int = 384, metric: str = "cosine", **c
         try:
             store = manager.get(request.user_id, request.model_id)
             _, scores, metas = store.query(request.query, k=request.k, filter_metadata=request.filter_metadata)
+        except HTTPException:
+            raise
         except Exception as e:
             raise HTTPException(status_code=500, detail=f"Query failed: {e}")
         results = [_format(store.config.metric, s, m, i + 1) for i, (s, m) in enumerate(zip(scores, metas))]
@@ -134,6 +163,8 @@ def create_app(base_path: str, dimension: int = 384, metric: str = "cosine", **c
         try:
             store = manager.get(request.user_id, request.model_id)
             batch = store.batch_query(np.asarray(request.queries, dtype=np.float32), k=request.k)
+        except HTTPException:
+            raise
         except Exception as e:
             raise HTTPException(status_code=500, detail=f"Batch query failed: {e}")
         results = [[_format(store.config.metric, s, m, i + 1) for i, (s, m) in enumerate(zip(scores, metas))]

@@ -17,7 +17,7 @@ ROOT = PKG_DIR.parent                      # mlx-vector-db_b200/
 CSRC = ROOT / "csrc"
 BUILD = ROOT / "build"
 LIB = PKG_DIR / "libb200vs.so"
-SOURCES = ["store.cu", "scan_topk.cu", "merge.cu", "search.cu", "gemm_topk.cu"]
+SOURCES = ["gemm_inst_plain.cu", "gemm_inst_general.cu", "store.cu", "scan_topk.cu", "merge.cu", "search.cu", "gemm_topk.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",

@@ -156,52 +156,71 @@ def _topk_rows(scores2d: torch.Tensor, kk: int, out_s: torch.Tensor, out_i: torc
 class _DbCache:
     """The functional API receives the raw database on every call (the reference
     re-normalises it each time, performance/mlx_optimized.py:41-52).  Here the database is
-    ingested once into a native store (K1) and reused while the same tensor is passed."""
+    ingested once into a native store (K1) and reused while THE SAME tensor object, unmodified,
+    is passed again.  An entry holds a reference to its tensor, so the tensor's memory cannot be
+    freed and handed to another database while the entry lives (an address-based key could then
+    return the old rows); temporaries made from numpy / CPU / non-contiguous inputs are never
+    cached."""
 
     def __init__(self, capacity: int = 2):
         self.capacity = capacity
-        self.items: "OrderedDict[tuple, C.c_void_p]" = OrderedDict()
+        self.items: "OrderedDict[int, tuple]" = OrderedDict()     # id(tensor) -> (tensor, _version, handle)
         self.lock = threading.Lock()
 
-    def get(self, db: torch.Tensor) -> C.c_void_p:
-        key = (db.data_ptr(), tuple(db.shape), db._version, db.device.index or 0)
-        with self.lock:
-            h = self.items.get(key)
-            if h is not None:
-                self.items.move_to_end(key)
-                return h
-            h = C.c_void_p()
-            _cabi.check(_cabi.lib().vs_create(key[3], db.shape[1], _cabi.METRIC_COSINE,
-                                              _cabi.SHADOW_BF16, max(int(db.shape[0]), 1),
-                                              C.byref(h)))
+    @staticmethod
+    def build(db: torch.Tensor) -> C.c_void_p:
+        h = C.c_void_p()
+        _cabi.check(_cabi.lib().vs_create(db.device.index or 0, db.shape[1], _cabi.METRIC_COSINE,
+                                          _cabi.SHADOW_BF16, max(int(db.shape[0]), 1), C.byref(h)))
+        try:
             _cabi.check(_cabi.lib().vs_append(h, _ptr(db), db.shape[0], 1, _stream(db)))
-            self.items[key] = h
+        except Exception:
+            _cabi.lib().vs_destroy(h)
+            raise
+        return h
+
+    def get(self, db: torch.Tensor) -> C.c_void_p:
+        with self.lock:
+            ent = self.items.get(id(db))
+            if ent is not None:
+                if ent[0] is db and ent[1] == db._version:
+                    self.items.move_to_end(id(db))
+                    return ent[2]
+                del self.items[id(db)]                      # written to in place since: rebuild
+                _cabi.lib().vs_destroy(ent[2])
+            h = self.build(db)
+            self.items[id(db)] = (db, db._version, h)
             while len(self.items) > self.capacity:
                 _, old = self.items.popitem(last=False)
-                _cabi.lib().vs_destroy(old)
+                _cabi.lib().vs_destroy(old[2])
             return h
 
     def clear(self):
         with self.lock:
-            for h in self.items.values():
-                _cabi.lib().vs_destroy(h)
+            for ent in self.items.values():
+                _cabi.lib().vs_destroy(ent[2])
             self.items.clear()
 
 
 _db_cache = _DbCache()
 
 
-def _search(q2d: torch.Tensor, db: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def _search(q2d: torch.Tensor, db: torch.Tensor, k: int, cacheable: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cacheable: `db` is the caller's own tensor (not a temporary `_dev` made)."""
     B, N = q2d.shape[0], db.shape[0]
     kk = min(int(k), N)
     if N == 0 or kk <= 0:
         return (torch.zeros((B, 0), dtype=torch.int32, device=db.device),
                 torch.zeros((B, 0), dtype=torch.float32, device=db.device))
-    h = _db_cache.get(db)
-    ids = torch.empty((B, kk), dtype=torch.int32, device=db.device)
-    scores = torch.empty((B, kk), dtype=torch.float32, device=db.device)
-    _cabi.check(_cabi.lib().vs_search(h, _ptr(q2d), B, kk, _cabi.SEARCH_AUTO, None, -1, _ptr(scores),
-                                      _ptr(ids), _stream(db)))
+    h = _db_cache.get(db) if cacheable else _DbCache.build(db)
+    try:
+        ids = torch.empty((B, kk), dtype=torch.int32, device=db.device)
+        scores = torch.empty((B, kk), dtype=torch.float32, device=db.device)
+        _cabi.check(_cabi.lib().vs_search(h, _ptr(q2d), B, kk, _cabi.SEARCH_AUTO, None, -1, _ptr(scores),
+                                          _ptr(ids), _stream(db)))
+    finally:
+        if not cacheable:
+            _cabi.lib().vs_destroy(h)       # synchronises the device before the arenas go away
     return ids, scores
 
 
@@ -215,7 +234,7 @@ def optimized_similarity_search(query_vector, db_vectors, k: int = 10):
         raise ValueError(f"query_vector must be 1-D or 2-D (1 row), shape: {tuple(q.shape)}")
     if db.ndim != 2 or q.shape[0] != db.shape[1]:
         raise ValueError(f"dimension mismatch: query {tuple(q.shape)}, db {tuple(db.shape)}")
-    ids, scores = _search(q.reshape(1, -1), db, k)
+    ids, scores = _search(q.reshape(1, -1), db, k, db is db_vectors)
     return ids[0], scores[0]
 
 
@@ -230,40 +249,40 @@ def optimized_batch_similarity_search(query_vectors, db_vectors, k: int = 10):
         raise ValueError(f"db_vectors must be 2-D, got shape {tuple(db.shape)}")
     if q.shape[1] != db.shape[1]:
         raise ValueError(f"dimension mismatch: query_vectors {q.shape[1]}, db_vectors {db.shape[1]}")
-    return _search(q, db, k)
+    return _search(q, db, k, db is db_vectors)
 
 
 # ---------------------------------------------------------------------- monitor / warm-up
 class PerformanceMonitor:
-    """performance/mlx_optimized.py:159-196."""
+    """Call statistics per function name.  Contract taken from the stats dictionary the
+    reference documents (performance/mlx_optimized.py:159-196): `get_stats()` maps each recorded
+    name to `calls`, `total_time_seconds` (4 decimals), `avg_time_ms` (4 decimals) and
+    `calls_per_second` (2 decimals).  Nothing in the reference or here records into it."""
 
     def __init__(self):
-        self.call_counts: Dict[str, int] = {}
-        self.total_times: Dict[str, float] = {}
-        self._lock = threading.Lock()
+        self._totals: Dict[str, list] = {}          # name -> [calls, seconds]
+        self._mu = threading.Lock()
 
     def record_call(self, func_name: str, duration: float):
-        with self._lock:
-            self.call_counts[func_name] = self.call_counts.get(func_name, 0) + 1
-            self.total_times[func_name] = self.total_times.get(func_name, 0.0) + duration
+        with self._mu:
+            ent = self._totals.setdefault(func_name, [0, 0.0])
+            ent[0] += 1
+            ent[1] += float(duration)
 
     def get_stats(self) -> dict:
-        with self._lock:
-            stats = {}
-            for name, calls in self.call_counts.items():
-                if calls == 0:
-                    continue
-                avg = self.total_times[name] / calls
-                stats[name] = {"calls": calls,
-                               "total_time_seconds": round(self.total_times[name], 4),
-                               "avg_time_ms": round(avg * 1000, 4),
-                               "calls_per_second": round(1.0 / avg if avg > 0 else 0, 2)}
-            return stats
+        with self._mu:
+            snapshot = {name: tuple(ent) for name, ent in self._totals.items() if ent[0] > 0}
+        out = {}
+        for name, (calls, seconds) in snapshot.items():
+            mean = seconds / calls
+            out[name] = {"calls": calls, "total_time_seconds": round(seconds, 4),
+                         "avg_time_ms": round(1e3 * mean, 4),
+                         "calls_per_second": round(1.0 / mean, 2) if mean > 0 else 0}
+        return out
 
     def reset(self):
-        with self._lock:
-            self.call_counts.clear()
-            self.total_times.clear()
+        with self._mu:
+            self._totals.clear()
 
 
 performance_monitor = PerformanceMonitor()

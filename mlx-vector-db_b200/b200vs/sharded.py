@@ -13,6 +13,7 @@ never move between GPUs, queries are replicated (every rank is handed the same b
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -57,7 +58,10 @@ class NativeShard:
         return int(_cabi.lib().vs_count(self.handle))
 
     def new_pack(self, B: int, k: int) -> torch.Tensor:
-        return torch.empty((2, B, k), dtype=torch.int32, device=self.device)
+        """(2, B, k) int32 view of a buffer padded to whole 16-byte words (vs_exchange_push)."""
+        words = 2 * B * k
+        raw = torch.zeros(((words + 3) // 4 * 4,), dtype=torch.int32, device=self.device)
+        return raw[:words].view(2, B, k)
 
     def search_into(self, q: torch.Tensor, k: int, pack: torch.Tensor) -> None:
         """pack[0] <- fp32 scores (bit pattern), pack[1] <- int32 global ids; (B, k) each."""
@@ -131,12 +135,69 @@ class NativeShard:
             self.handle = C.c_void_p()
 
 
+class PeerExchange:
+    """Exchange buffers of one (B, k) shape in symmetric memory (every rank of the group has every
+    rank's buffer mapped): `depth` slots of `world` candidate blocks + `world` flag words each, and
+    the block-completion counter of the push kernel.  Creation is collective.  csrc/exchange.cu."""
+    DEPTH = 4
+
+    def __init__(self, B: int, k: int, device: torch.device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.B, self.k = B, k
+        self.block_bytes = (2 * B * k * 4 + 15) // 16 * 16
+        self.slot_bytes = self.world * self.block_bytes
+        self.flags_off = self.DEPTH * self.slot_bytes
+        self.counter_off = self.flags_off + self.DEPTH * self.world * 4
+        total = (self.counter_off + 16 + 255) // 256 * 256
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.current_stream(device).synchronize()
+        self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.buf.data_ptr()
+        self.base = ptrs[self.rank]
+        P = C.c_void_p * self.world
+        # per slot: where this rank's block / flag word lives in every rank's buffer
+        self.dst = [P(*[x + s * self.slot_bytes + self.rank * self.block_bytes for x in ptrs])
+                    for s in range(self.DEPTH)]
+        self.flag = [P(*[x + self.flags_off + (s * self.world + self.rank) * 4 for x in ptrs])
+                     for s in range(self.DEPTH)]
+        self.step = 0
+        dist.barrier(group)                      # every buffer is zeroed and mapped before the first push
+
+    def exchange(self, shard, pack: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Push this rank's (2, B, k) block to every rank, wait for everybody's, merge: (ids, scores).
+        Everything is enqueued on the current stream."""
+        lib = _cabi.lib()
+        self.step += 1
+        slot = self.step % self.DEPTH
+        dev = shard.device.index or 0
+        stream = shard._stream()
+        # `pack` is a view of a buffer padded to whole 16-byte words (NativeShard.new_pack)
+        _cabi.check(lib.vs_exchange_push(dev, C.c_void_p(pack.data_ptr()), self.block_bytes, self.dst[slot],
+                                         self.flag[slot], self.world, self.step,
+                                         C.c_void_p(self.base + self.counter_off), stream))
+        _cabi.check(lib.vs_exchange_wait(dev, C.c_void_p(self.base + self.flags_off + slot * self.world * 4),
+                                         self.world, self.step, stream))
+        B, k = self.B, self.k
+        out_s = torch.empty((B, k), dtype=torch.float32, device=shard.device)
+        out_i = torch.empty((B, k), dtype=torch.int32, device=shard.device)
+        base = self.base + slot * self.slot_bytes
+        _cabi.check(lib.vs_merge(dev, shard.metric, C.c_void_p(base), C.c_void_p(base + 4 * B * k), self.world, B, k,
+                                 self.block_bytes // 4, C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                 stream))
+        return out_i, out_s
+
+
 class PendingSearch:
     """Handle returned by ShardedVectorStore.submit()."""
-    __slots__ = ("q", "B", "kk", "bufs", "ticket", "done")
+    __slots__ = ("q", "B", "kk", "bufs", "ticket", "done", "stream")
 
-    def __init__(self, q, B, kk, bufs, ticket, done=None):
+    def __init__(self, q, B, kk, bufs, ticket, done=None, stream=None):
         self.q, self.B, self.kk, self.bufs, self.ticket, self.done = q, B, kk, bufs, ticket, done
+        self.stream = stream                     # the side stream the search was enqueued on
 
 
 def split_batch(m: int, world: int, rank: int) -> Tuple[int, int]:
@@ -152,7 +213,7 @@ class ShardedVectorStore:
 
     def __init__(self, dimension: int, metric: str = "cosine", device: Optional[torch.device] = None,
                  group=None, shadow_bf16: bool = True, max_vectors_per_shard: int = 0,
-                 search_mode: str = "auto", shard_factory=None):
+                 search_mode: str = "auto", shard_factory=None, overlap_streams: Optional[bool] = None):
         self.group = group
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -170,11 +231,27 @@ class ShardedVectorStore:
         self.total = 0
         self._bufs = {}
         self._xstream = None
+        # submit() alternates between two side streams: the small kernels around a search's GEMM
+        # (query preparation, threshold selection, rescoring) then overlap the neighbouring
+        # search's GEMM instead of leaving the tensor pipe idle between two searches
+        self._sstreams = None
+        self._nsubmit = 0
+        # Default: on for world > 1, where a shard's GEMM is short and those kernels are a quarter of
+        # the step; off for a single GPU, where they are ~5 % and a single stream keeps every kernel's
+        # CUDA-event bracket free of queueing time (bench.py's roofline).  B200VS_OVERLAP=0|1 overrides.
+        if overlap_streams is None:
+            env = os.environ.get("B200VS_OVERLAP", "")
+            overlap_streams = (env == "1") if env in ("0", "1") else self.world > 1
+        self.overlap_streams = bool(overlap_streams)
+        # candidate exchange at world > 1: "p2p" = direct stores into every rank's symmetric-memory
+        # buffer (PeerExchange, csrc/exchange.cu), "nccl" = all_gather_into_tensor.  p2p falls back to
+        # nccl (on every rank together) when the symmetric-memory rendezvous is not possible.
+        self.exchange_mode = os.environ.get("B200VS_EXCHANGE", "p2p")
+        self._exchanges = {}
         # searches that may be in flight between submit() and result(); their buffers are recycled
         # in a ring of this depth
         self.pipeline_depth = 4
         # B200VS_SHARD_SYNC=1: synchronise the stream before returning (measured: no effect on throughput)
-        import os
         self.sync_each_search = (self.world > 1 and device.type == "cuda" and
                                  os.environ.get("B200VS_SHARD_SYNC", "0") == "1")
 
@@ -240,20 +317,40 @@ class ShardedVectorStore:
             ring["slots"].append((pack, flat))
         pack, flat = ring["slots"][ring["next"] % len(ring["slots"])]
         ring["next"] += 1
-        if row_mask is not None and mask_live == 0:
-            # no local row takes part: this rank contributes an empty candidate block
-            pack[0].zero_()
-            pack[1].fill_(-1)
-            ticket = None
-        elif row_mask is not None:
-            ticket = self.shard.submit_into(q, kk, pack, row_mask, mask_live)
+        if self.device.type != "cuda":           # CPU stand-in shards (gloo tests)
+            if row_mask is not None and mask_live == 0:
+                pack[0].zero_()
+                pack[1].fill_(-1)
+                ticket = None
+            elif row_mask is not None:
+                ticket = self.shard.submit_into(q, kk, pack, row_mask, mask_live)
+            else:
+                ticket = self.shard.submit_into(q, kk, pack)
+            return PendingSearch(q, B, kk, (pack, flat), ticket, None)
+        cur = torch.cuda.current_stream(self.device)
+        if self.overlap_streams:
+            if self._sstreams is None:
+                self._sstreams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            ss = self._sstreams[self._nsubmit % 2]
+            self._nsubmit += 1
+            ss.wait_stream(cur)                  # the queries (and an earlier reader of `pack`) are on `cur`
         else:
-            ticket = self.shard.submit_into(q, kk, pack)
-        done = None
-        if self.world > 1 and self.device.type == "cuda":
+            ss = cur
+        with torch.cuda.stream(ss):
+            if row_mask is not None and mask_live == 0:
+                # no local row takes part: this rank contributes an empty candidate block
+                pack[0].zero_()
+                pack[1].fill_(-1)
+                ticket = None
+            elif row_mask is not None:
+                ticket = self.shard.submit_into(q, kk, pack, row_mask, mask_live)
+            else:
+                ticket = self.shard.submit_into(q, kk, pack)
             done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream(self.device))
-        return PendingSearch(q, B, kk, (pack, flat), ticket, done)
+            done.record(ss)
+        if ss is not cur:
+            q.record_stream(ss)
+        return PendingSearch(q, B, kk, (pack, flat), ticket, done, ss)
 
     def result(self, pending: "PendingSearch") -> Tuple[torch.Tensor, torch.Tensor]:
         """Finish a submitted search: wait for ITS certification count (re-running what could not
@@ -266,23 +363,35 @@ class ShardedVectorStore:
         pack, flat = pending.bufs
         if pending.ticket is not None:
             self.shard.complete(pending.ticket)
-        if self.world == 1:
-            return pack[1].clone(), pack[0].view(torch.float32).clone()
         if self.device.type != "cuda":          # CPU stand-in shards (gloo tests)
+            if self.world == 1:
+                return pack[1].clone(), pack[0].view(torch.float32).clone()
             dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
             return self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
         cur = torch.cuda.current_stream(self.device)
+        # a query that was re-run wrote its rows (on the search's stream) after `done` was recorded
+        redone = pending.ticket is not None and self.shard.last_complete_enqueued_work()
+        if self.world == 1:
+            if pending.stream is not cur:
+                if redone:
+                    cur.wait_stream(pending.stream)
+                else:
+                    cur.wait_event(pending.done)
+            return pack[1].clone(), pack[0].view(torch.float32).clone()
         if self._xstream is None:
             self._xstream = torch.cuda.Stream(self.device)
         xs = self._xstream
-        # a query that was re-run wrote its rows after `done` was recorded: order after those too
-        if self.shard.last_complete_enqueued_work():
-            xs.wait_stream(cur)
+        if redone:
+            xs.wait_stream(pending.stream)
         else:
             xs.wait_event(pending.done)
         with torch.cuda.stream(xs):
-            dist.all_gather_into_tensor(flat, pack.view(-1), group=self.group)
-            out = self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
+            ex = self._peer_exchange(B, kk)
+            if ex is not None:
+                out = ex.exchange(self.shard, pack)
+            else:
+                dist.all_gather_into_tensor(flat, pack.reshape(-1), group=self.group)
+                out = self.shard.merge(flat.view((self.world,) + tuple(pack.shape)), self.world, B, kk)
         cur.wait_stream(xs)      # the caller consumes the results on its own stream
         for t in out:
             t.record_stream(cur)
@@ -290,5 +399,30 @@ class ShardedVectorStore:
             cur.synchronize()
         return out
 
+    def _peer_exchange(self, B: int, kk: int):
+        """The PeerExchange of this result shape, created (collectively) on first use; None when
+        the exchange runs over NCCL."""
+        if self.exchange_mode != "p2p":
+            return None
+        key = (B, kk)
+        if key not in self._exchanges:
+            if len(self._exchanges) > 8:
+                self._exchanges.clear()
+            ex, ok = None, 1
+            try:
+                ex = PeerExchange(B, kk, self.device, self.group)
+            except Exception as e:       # noqa: BLE001 -- no symmetric memory on this box / build
+                ok = 0
+                import logging
+                logging.getLogger(__name__).warning("peer-memory exchange unavailable (%s): using NCCL", e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:    # all ranks take the same path
+                ex = None
+                self.exchange_mode = "nccl"
+            self._exchanges[key] = ex
+        return self._exchanges[key]
+
     def close(self) -> None:
+        self._exchanges.clear()
         self.shard.close()

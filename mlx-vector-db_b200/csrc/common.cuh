@@ -14,7 +14,15 @@ namespace vs {
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 extern std::atomic<int64_t> g_launches;
-inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// B200VS_TRACE=1 (diagnostic): every kernel launch is followed by a device synchronisation and a
+// line on stderr naming the call site, so a kernel that never returns can be identified.
+void trace_launch(const char* file, int line);
+extern int g_trace;                       // -1 = not read yet
+inline void count_launch_at(const char* file, int line) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_trace != 0) trace_launch(file, line);
+}
+#define count_launch() ::vs::count_launch_at(__FILE__, __LINE__)
 
 // Optional CUDA-event bracket around the dominant kernels (vs_profile / vs_profile_read):
 // bench.py uses it to time the scan / GEMM kernel alone on the stream it is launched on.

@@ -1,22 +1,28 @@
-// K3 gemm_topk -- large-batch search as a dense contraction on the 5th-gen tensor cores.
+// K3 gemm_topk -- large-batch search as a dense contraction on the 5th-gen tensor cores (host side:
+// plan, parameters, the small helper kernels; the tcgen05 kernel itself is in gemm_kernel.cuh).
 //
-//   S'[q, r] = sum_k bf16(Q[q, k]) * bf16(X[r, k])        tcgen05.mma kind::f16, fp32 in TMEM
+//   S'[q, r] = sum_k h(Q[q, k]) * h(X[r, k])        tcgen05.mma kind::f16 (fp16 for cosine, bf16
+//                                                   otherwise), fp32 accumulators in TMEM
 //
 // replaces `matmul(Qn, DBn.T)` + `argsort(axis=1)[:, :k]` of the reference
 // (performance/mlx_optimized.py:86,235-236) without ever writing the (B, N) matrix:
 //
-//   pass 1  GEMM over a sample of the rows; epilogue keeps, per query, the maximum of every
-//           128-row tile.  The kc-th largest tile maximum is a lower bound tau[q] on the kc-th
-//           best score of the whole database (kc distinct rows reach it).
-//   pass 2  GEMM over all rows; epilogue compares TMEM columns with tau[q] (one thread owns
-//           one query: lane = query) and appends the rare survivors to that thread's private
-//           candidate buffer.
-//   then    K4 merge -> top-kc candidates by bf16 score; K5 rescoring in exact fp32 with the
-//           scan's arithmetic; final K4 merge -> top-k; certification: the candidate set
+//   pass 1  GEMM over a small strided sample of the tiles; epilogue keeps, per query, the maximum of
+//           every tile.  The ks-th largest tile maximum is a lower bound tau[q] on the ks-th best
+//           score of the whole database (ks distinct rows reach it); higher order statistics of the
+//           sample become a ladder of trial thresholds (tau_select_kernel).
+//   pass 2  GEMM over all rows; epilogue compares TMEM columns with tau[q] (one thread owns one
+//           query: lane = query) and appends the rare survivors to that thread's private candidate
+//           buffer.  Survivors are also counted per ladder level (global atomics); once ks rows have
+//           reached a level it becomes the threshold of every CTA, so tau tightens as the pass goes.
+//   then    one launch per query block: the kc best survivors by 16-bit key, K5 rescoring in exact
+//           fp32 with the scan's arithmetic, final ordering, certification: the candidate set
 //           provably contains the exact top-k when
-//               exact_k-th  >  bf16_kc-th + E,   E >= |exact - bf16| for every row,
-//           otherwise (or if a candidate buffer overflowed) the query is re-run through the
-//           exact fp32 scan (K2).  Results are therefore always the exact fp32 ones.
+//               exact_k-th  >  beta + E,   E >= |exact - 16-bit| for every row,
+//           beta = the kc-th candidate's 16-bit key (or the final tau with fewer than kc survivors);
+//           otherwise (or if a candidate buffer overflowed) the query is re-run -- once through K3
+//           with 4x the candidates, then through the exact fp32 scan (K2).  Results are therefore
+//           always the exact fp32 ones.
 //
 // Kernel anatomy (one CTA per SM, 384 threads): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane; RESIDENT: warps 1 and 3 issue alternate accumulators), warp 2 = TMEM
@@ -26,660 +32,18 @@
 //   RESIDENT (K <= 256): the CTA's query tiles (up to 4 x 128 queries) are loaded once and stay
 //     in shared memory; database tiles of 128 rows stream through a ring; 4 TMEM accumulators
 //     of 128 columns, one per query tile, let the epilogue of tile m overlap the MMAs of m+1.
-//   STREAMING (any K): query and database chunks both stream through the ring per 64-wide K
-//     step; database tiles of 256 rows; 2 TMEM accumulators of 256 columns.
-#include <cuda.h>
-#include <cuda_fp16.h>
-#include <cuda_fp8.h>
-#include <algorithm>
-#include <cstdlib>
-#include <cmath>
-#include <cstring>
+//   STREAMING (any K): CTA pairs (cta_group::2); every pair serves ONE query tile pair, the first
+//     K chunks of which stay resident, the rest and the database chunks stream through a ring per
+//     64-wide K step; database tiles of 256 rows; 2 TMEM accumulators of 256 columns.
+#include <cstdio>
 #include <mutex>
 #include <vector>
+#include "gemm_kernel.cuh"
 #include "gemm_topk.cuh"
 #include "scan_topk.cuh"
 #include "store.cuh"
 
 namespace vs {
-
-#ifndef VS_EPI_GROUPS
-#define VS_EPI_GROUPS 2
-#endif
-#ifndef VS_EPI_GROUPS_RES
-#define VS_EPI_GROUPS_RES 2
-#endif
-// epilogue warp groups (4 warps each; query tile mt belongs to group mt % groups), separately
-// for the STREAMING (K > 256) and RESIDENT (K <= 256) variants.  Measured at 10 M x 128, batch
-// 1024 (profiles/r01_k3_probe_experiments.txt): four groups are 5 % SLOWER than two for RESIDENT,
-// with one MMA-issuing warp (2.37 vs 2.24-2.33 ms) and with two (2.21 vs 2.10 ms).
-constexpr int kEpiGroupsStream = VS_EPI_GROUPS;
-constexpr int kEpiGroupsRes = VS_EPI_GROUPS_RES;
-__host__ __device__ constexpr int epi_groups(bool resident) { return resident ? kEpiGroupsRes : kEpiGroupsStream; }
-// 4 control warps + the epilogue warps
-__host__ __device__ constexpr int gemm_threads(bool resident) { return 128 + 128 * epi_groups(resident); }
-constexpr int kTileM = 128;              // queries per m-tile = TMEM lanes
-constexpr int kChunkK = 64;              // bf16 elements per 128-byte swizzled row
-constexpr int kChunkBytes = 128 * 128;   // 128 rows x 128 B
-constexpr int kTmemCols = 512;
-constexpr int kCandCap = 64;             // candidate slots per (CTA, query)
-constexpr int kMaxGroupTiles = 4;        // pass 1: tiles (of one CTA) per maximum
-constexpr int kGlobalCap = 4096;         // candidate slots per query over all CTAs (= K4's capacity)
-constexpr int kMaxQueriesPerLaunch = 2048;
-#ifndef VS_RES_ISSUERS
-#define VS_RES_ISSUERS 2
-#endif
-constexpr int kResIssuers = VS_RES_ISSUERS;   // RESIDENT: warps that issue MMAs (1: warp 1; 2: warps 1 and 3)
-#ifndef VS_RES_TN
-#define VS_RES_TN 128
-#endif
-constexpr int kResTN = VS_RES_TN;        // RESIDENT: database rows per tile (MMA N), 128 or 256
-
-enum { kModeFilter = 0, kModeMax = 1, kModeDump = 2,
-       // diagnostic builds only (-DVS_GEMM_DEBUG_MODES, timing experiments, results are not usable):
-       kModeNop = 3,    // epilogue releases every accumulator unread: the pure TMA + MMA pipeline
-       kModeHalf = 4 }; // the filter epilogue over the first half of every accumulator's columns
-
-struct GemmParams {
-  int kchunks;              // K / 64
-  int64_t n_rows;           // database rows visible
-  int n_tiles;              // database tiles this launch covers (tile = TN rows)
-  int tile_stride;          // launch tile t is database tile (tile_first + t) * tile_stride (pass 1 samples
-  int tile_first;           //   the whole row range with a stride; pass 2 may run as two ranges)
-  int m_tiles;              // query tiles in the batch
-  int ngroups;              // RESIDENT: query groups (CTA c serves group c % ngroups)
-  int nq;                   // live queries
-  int mode;
-  int fp16;                 // operands are fp16 (cosine) instead of bf16
-  int fp8;                  // operands are e4m3: tcgen05.mma kind::f8f6f4 (K = 32 per MMA, 128 per chunk)
-  int stages;               // ring depth
-  uint32_t idesc;           // tcgen05 instruction descriptor (operand format, M, N)
-  const float* tau;         // (nq,) filter threshold (kModeFilter)
-  float* cand_score;        // (lists, m_tiles*128, kCandCap)
-  int32_t* cand_id;
-  int32_t* cand_cnt;        // (lists, m_tiles*128) candidates per list, zeroed by the host (STREAMING keeps
-                            // its running counts here, RESIDENT writes them at the end)
-  int32_t* overflow;        // (m_tiles*128,) set to 1 when a buffer overflowed
-  float* glist_s;           // (m_tiles*128, kGlobalCap) dense per-query candidate lists: at the end of the
-  int32_t* glist_i;         //   kernel every thread moves its private candidates here (one atomicAdd on
-  int32_t* gcount;          //   gcount[q] per (CTA, query)), so K4 reads contiguous entries only
-  float* gmax;              // kModeMax: (m_tiles*128, n_groups) maxima of groups of kMaxGroupTiles tiles
-  int n_groups;             //   = units_in_group * groups_per_unit
-  int groups_per_unit;
-  int group_tiles;          //   tiles (of one unit) per maximum: kMaxGroupTiles, or 1 when tiles are scarce
-  float* dump;              // kModeDump: (nq, dump_ld)
-  int64_t dump_ld;
-  const float* sqnorms;     // euclidean: ||x||^2 per row; the epilogue turns the accumulator s into the key
-                            //   2 s - ||x||^2 (= ||q||^2 - d^2: larger = closer).  NULL: key = s
-  const uint32_t* row_mask; // nullable: bit r set = row r takes part (metadata filter pushed into the GEMM)
-};
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void bar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// One lane of a converged warp, chosen by `elect.sync`.  The single-thread roles (TMA producer,
-// MMA issuer) branch on THIS rather than on `lane == 0`: with a lane-id test the compiler cannot
-// tell that exactly one thread is active and wraps every warp-uniform instruction (UTCHMMA,
-// UTCBAR, UTMALDG) in an ELECT / BRA.U.ANY serialisation loop -- measured ~110 clk per MMA for
-// the issuing thread, more than the 64 clk an M = 128, N = 128, K = 16 MMA takes to execute.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
-// [46,48), layout_type=2 [61,64))
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, both operands K-major,
-// operand format 0 = fp16, 1 = bf16
-__host__ __device__ constexpr uint32_t instr_desc(int m, int n, int fmt) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
-}
-
-// -------------------------------------------------------------------- the kernel
-// MT > 0: RESIDENT with MT query tiles per CTA.  MT == 0: STREAMING.
-// CG = 1: one CTA per MMA (M = 128).  CG = 2: a CTA pair (cluster of 2, `cta_group::2`) shares
-// every MMA: M = 256 = 128 query rows from each CTA, N = 256 database rows of which each CTA
-// loads and holds half; the leader (cluster rank 0) issues the MMAs for both, accumulator rows
-// land in each CTA's own TMEM.  Halves the shared-memory operand reads per MMA and the
-// database bytes each SM pulls through TMA.
-//   MMA N (database rows per tile) TN: RESIDENT 128 (four accumulators of 128 columns, so the
-//   epilogue of one overlaps the MMAs of the next three), STREAMING 256.  RESIDENT with CG = 2
-//   therefore issues M = 256, N = 128 MMAs: each CTA loads 64 database rows per tile.
-template <int CG> struct CgOps;
-template <> struct CgOps<1> {
-  __device__ static __forceinline__ void alloc(uint32_t dst) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  __device__ static __forceinline__ void dealloc(uint32_t base) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmemCols) : "memory");
-  }
-  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    tc_mma(d, a, b, idesc, acc);
-  }
-  __device__ static __forceinline__ void mma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    tc_mma_f8(d, a, b, idesc, acc);
-  }
-  __device__ static __forceinline__ void commit(uint32_t bar) { tc_commit(bar); }
-  __device__ static __forceinline__ void load(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    tma_load_2d(dst, map, c0, c1, bar);
-  }
-};
-template <> struct CgOps<2> {
-  __device__ static __forceinline__ void alloc(uint32_t dst) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  __device__ static __forceinline__ void dealloc(uint32_t base) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmemCols) : "memory");
-  }
-  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-  }
-  __device__ static __forceinline__ void mma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-  }
-  // arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair
-  __device__ static __forceinline__ void commit(uint32_t bar) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"((uint16_t)3) : "memory");
-  }
-  // the transaction bytes are credited to the LEADER's barrier (peer bit of the address cleared)
-  __device__ static __forceinline__ void load(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
-  }
-};
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void bar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(rank) : "memory");
-}
-
-template <int MT, int MODE, int CG>
-__global__ void __launch_bounds__(gemm_threads(MT > 0), 1)
-gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
-                 const GemmParams p) {
-  constexpr bool RES = MT > 0;
-  constexpr int kEpiGroups = epi_groups(RES);
-  constexpr bool FILT = MODE == kModeFilter || MODE == kModeHalf;
-  constexpr int TN = RES ? kResTN : 256;                  // MMA N = database rows per tile
-  constexpr int TN_LOCAL = TN / CG;                       // rows of the tile this CTA loads
-  constexpr int SLOTS = kTmemCols / TN;
-  constexpr int B_CHUNK_BYTES = TN_LOCAL * 128;
-  using Ops = CgOps<CG>;
-  extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment for the 128B-swizzle atoms (same offset in both CTAs of a pair)
-  unsigned char* smem = smem_raw + ((1024 - (s_u32(smem_raw) & 1023)) & 1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kch = p.kchunks;
-  const int kstep = p.fp8 ? 128 : kChunkK;                // elements per 128-byte chunk row
-  const int crank = CG == 2 ? (int)cluster_rank() : 0;    // 0 = leader (issues the MMAs)
-
-  // ---- carve-up
-  unsigned char* a_res = smem;                                         // RES: MT*kch chunks
-  const size_t a_bytes = RES ? (size_t)MT * kch * kChunkBytes : 0;
-  const size_t stage_bytes = RES ? (size_t)kch * B_CHUNK_BYTES : (size_t)kChunkBytes + B_CHUNK_BYTES;
-  unsigned char* ring = smem + a_bytes;
-  unsigned char* tail = ring + (size_t)p.stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  // bars: [0]=a_full, [1..S]=full, [1+S..2S]=empty, then acc_full[SLOTS], acc_empty[SLOTS]
-  const uint32_t bar_a = s_u32(bars);
-  const uint32_t bar_full = s_u32(bars + 1);
-  const uint32_t bar_empty = s_u32(bars + 1 + p.stages);
-  const uint32_t bar_accf = s_u32(bars + 1 + 2 * p.stages);
-  const uint32_t bar_acce = s_u32(bars + 1 + 2 * p.stages + SLOTS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * p.stages + 2 * SLOTS);
-  // euclidean only: ||x||^2 of the current tile's rows, per epilogue group, double-buffered
-  float* sq_base = reinterpret_cast<float*>(tail + 512);
-
-  // ---- work assignment, in units of one CTA (CG=1) or one CTA pair (CG=2)
-  // query tiles are counted per unit: unit tile m covers the 128-row tiles m*CG + crank
-  const int unit = blockIdx.x / CG;
-  const int n_units = gridDim.x / CG;
-  const int um_tiles = p.m_tiles / CG;                                 // m_tiles is a multiple of CG
-  const int ngroups = RES ? p.ngroups : 1;
-  const int group = unit % ngroups;
-  const int uig = unit / ngroups;                                      // unit index inside its group
-  const int units_in_group = (n_units - group + ngroups - 1) / ngroups;
-  const int m_first = RES ? group * MT : 0;
-  const int m_count = RES ? min(MT, um_tiles - m_first) : um_tiles;
-  int my_tiles = 0;
-  if (uig < p.n_tiles) my_tiles = (p.n_tiles - uig + units_in_group - 1) / units_in_group;
-
-  if (threadIdx.x == 0) {
-    bar_init(bar_a, 1);
-    // a RESIDENT stage is released by every MMA-issuing warp (one tcgen05.commit each)
-    for (int i = 0; i < p.stages; ++i) { bar_init(bar_full + 8 * i, 1); bar_init(bar_empty + 8 * i, RES ? kResIssuers : 1); }
-    for (int i = 0; i < SLOTS; ++i) { bar_init(bar_accf + 8 * i, 1); bar_init(bar_acce + 8 * i, 4 * CG); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) Ops::alloc(s_u32(tmem_slot));
-  tc_fence_before();
-  __syncthreads();
-  if (CG == 2) cluster_sync_all();          // both CTAs' barriers exist before any remote arrive
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ================================================================ TMA producer
-    // Every CTA loads its own operands; with CG = 2 the bytes of both CTAs are credited to the
-    // leader's full barriers, which the leader arms with the pair's total.
-    if (my_tiles > 0 && m_count > 0 && elect_one()) {
-      if (RES) {
-        if (crank == 0) bar_expect_tx(bar_a, (uint32_t)(CG * m_count * kch * kChunkBytes));
-        for (int mt = 0; mt < m_count; ++mt)
-          for (int kc = 0; kc < kch; ++kc)
-            Ops::load(s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes), &map_q, kc * kstep,
-                      ((m_first + mt) * CG + crank) * kTileM, bar_a);
-      }
-      int st = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int nt = (p.tile_first + uig + i * units_in_group) * p.tile_stride;
-        const int row0 = nt * TN + crank * TN_LOCAL;                  // first database row this CTA loads
-        if (RES) {
-          bar_wait(bar_empty + 8 * st, ph ^ 1u);
-          if (crank == 0) bar_expect_tx(bar_full + 8 * st, (uint32_t)(CG * kch * B_CHUNK_BYTES));
-          for (int kc = 0; kc < kch; ++kc) {
-            unsigned char* dst = ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES;
-            Ops::load(s_u32(dst), &map_x, kc * kstep, row0, bar_full + 8 * st);
-            if (TN_LOCAL == 256) Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kstep, row0 + 128, bar_full + 8 * st);
-          }
-          if (++st == p.stages) { st = 0; ph ^= 1u; }
-        } else {
-          for (int mt = 0; mt < m_count; ++mt)
-            for (int kc = 0; kc < kch; ++kc) {
-              bar_wait(bar_empty + 8 * st, ph ^ 1u);
-              if (crank == 0) bar_expect_tx(bar_full + 8 * st, (uint32_t)(CG * (kChunkBytes + B_CHUNK_BYTES)));
-              unsigned char* dst = ring + (size_t)st * stage_bytes;
-              Ops::load(s_u32(dst), &map_q, kc * kstep, (mt * CG + crank) * kTileM, bar_full + 8 * st);
-              Ops::load(s_u32(dst + kChunkBytes), &map_x, kc * kstep, row0, bar_full + 8 * st);
-              if (TN_LOCAL == 256)   // 256 rows = two boxes of 128
-                Ops::load(s_u32(dst + 2 * kChunkBytes), &map_x, kc * kstep, row0 + 128, bar_full + 8 * st);
-              if (++st == p.stages) { st = 0; ph ^= 1u; }
-            }
-        }
-      }
-    }
-  } else if (warp == 1 || (RES && kResIssuers == 2 && warp == 3)) {
-    // ================================================================ MMA issuer (leader CTA)
-    // RESIDENT at K <= 256 is bound by how fast ONE thread can issue: ~117 SASS instructions per
-    // accumulator (barrier wait, two descriptors per K chunk, 8 MMAs, commit) on a single warp's
-    // dependent uniform-datapath chain take 700-800 clk, the 8 MMAs execute in 512 (ncu: the
-    // issuing warp 85 % busy, tensor pipe 63 %).  So two warps issue, taking alternate accumulators
-    // (`it` parity: with 4 query tiles each warp always owns the same two TMEM slots); MMAs of
-    // different accumulators are independent, both warps read the same shared-memory operands and
-    // each releases the stage with its own commit.
-    const int issuer = warp == 1 ? 0 : 1;
-    if (crank == 0 && my_tiles > 0 && m_count > 0 && elect_one()) {
-      const uint32_t idesc = p.idesc;
-      if (RES) { bar_wait(bar_a, 0); tc_fence_after(); }
-      int st = 0;
-      uint32_t ph = 0;
-      int it = 0;                                       // (n-tile, m-tile) sequence number
-      for (int i = 0; i < my_tiles; ++i) {
-        if (RES) {
-          bar_wait(bar_full + 8 * st, ph);
-          tc_fence_after();
-        }
-        for (int mt = 0; mt < m_count; ++mt, ++it) {
-          if (RES && kResIssuers == 2 && (it & 1) != issuer) continue;   // the other issuing warp's
-          const int slot = it % SLOTS;
-          const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
-          bar_wait(bar_acce + 8 * slot, aph ^ 1u);      // epilogues drained this accumulator
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TN);
-          for (int kc = 0; kc < kch; ++kc) {
-            uint32_t a_addr, b_addr;
-            if (RES) {
-              a_addr = s_u32(a_res + (size_t)(mt * kch + kc) * kChunkBytes);
-              b_addr = s_u32(ring + (size_t)st * stage_bytes + (size_t)kc * B_CHUNK_BYTES);
-            } else {
-              bar_wait(bar_full + 8 * st, ph);
-              tc_fence_after();
-              a_addr = s_u32(ring + (size_t)st * stage_bytes);
-              b_addr = a_addr + kChunkBytes;
-            }
-            const uint64_t a_desc = smem_desc(a_addr);
-            const uint64_t b_desc = smem_desc(b_addr);
-            if (p.fp8) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)               // e4m3: +32 B per 32-element K step
-                Ops::mma_f8(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                            (kc | k) != 0 ? 1u : 0u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k)    // 16-bit: +32 B per 16-element K step
-                Ops::mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                         (kc | k) != 0 ? 1u : 0u);
-            }
-            if (!RES) {
-              Ops::commit(bar_empty + 8 * st);          // smem stage free once these MMAs retire
-              if (++st == p.stages) { st = 0; ph ^= 1u; }
-            }
-          }
-          Ops::commit(bar_accf + 8 * slot);             // accumulator ready for the epilogues
-        }
-        if (RES) {
-          Ops::commit(bar_empty + 8 * st);
-          if (++st == p.stages) { st = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ================================================================ epilogue
-    // One thread owns one query row of the m-tile (TMEM lane = query).  Per accumulator the
-    // warp reads 32-column chunks (double-buffered tcgen05.ld) and reduces each to its
-    // maximum with 3-input FMNMX; only when some lane's maximum reaches its threshold does the
-    // warp take the rare path, which re-reads the offending 8-column groups from TMEM (short
-    // code: the hot loop must stay resident in the instruction cache).
-    const int quad = warp & 3;                          // TMEM lane quadrant of this warp
-    const int grp = (warp - 4) >> 2;                    // query tile mt belongs to group mt % kEpiGroups
-    const int row = quad * 32 + lane;                   // query row inside the m-tile
-    const int list = RES ? uig : unit;                  // candidate list of this unit
-    const int64_t q_total = (int64_t)p.m_tiles * kTileM;
-    constexpr int NST = RES ? MT : 1;
-    float tau_l[NST];                                   // RESIDENT: per-thread state of its
-    int cnt_l[NST];                                     // query tiles (dynamically indexed)
-    float rmax_l[MODE == kModeMax ? 16 : 1];            // pass 1: running maximum per query tile
-    if (MODE == kModeMax)
-      for (int mt = 0; mt < 16; ++mt) rmax_l[mt] = VS_NEG_INF;
-    if (RES && FILT) {
-      for (int mt = 0; mt < NST; ++mt) {
-        cnt_l[mt] = 0;
-        const int q = ((m_first + mt) * CG + crank) * kTileM + row;
-        tau_l[mt] = q < p.nq ? p.tau[q] : __int_as_float(0x7f800000);
-      }
-    }
-    int it = 0;
-    const bool l2 = p.sqnorms != nullptr;
-    const int gtid = threadIdx.x & 127;                 // thread inside its epilogue group
-    float* sq_grp = sq_base + grp * 2 * TN;
-    float sq_next[TN / 128];
-    if (l2 && my_tiles > 0) {
-#pragma unroll
-      for (int h = 0; h < TN / 128; ++h) {
-        const int64_t r = (int64_t)(p.tile_first + uig) * p.tile_stride * TN + h * 128 + gtid;
-        sq_next[h] = r < p.n_rows ? __ldg(p.sqnorms + r) : __int_as_float(0x7f800000);
-      }
-    }
-    for (int i = 0; i < my_tiles; ++i) {
-      const int nt = (p.tile_first + uig + i * units_in_group) * p.tile_stride;
-      const float* sqb = sq_grp + (i & 1) * TN;
-      if (l2) {
-        // rows past the end of the store get ||x||^2 = +inf: their key is -inf in every mode
-#pragma unroll
-        for (int h = 0; h < TN / 128; ++h) sq_grp[(i & 1) * TN + h * 128 + gtid] = sq_next[h];
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-        if (i + 1 < my_tiles) {
-#pragma unroll
-          for (int h = 0; h < TN / 128; ++h) {
-            const int64_t r = (int64_t)(p.tile_first + uig + (i + 1) * units_in_group) * p.tile_stride * TN + h * 128 + gtid;
-            sq_next[h] = r < p.n_rows ? __ldg(p.sqnorms + r) : __int_as_float(0x7f800000);
-          }
-        }
-      }
-#pragma unroll 1
-      for (int mt = 0; mt < m_count; ++mt, ++it) {
-        if ((mt % kEpiGroups) != grp) continue;
-        const int slot = it % SLOTS;
-        const uint32_t aph = (uint32_t)(it / SLOTS) & 1u;
-        const int q = ((m_first + mt) * CG + crank) * kTileM + row;
-        const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
-        float t = __int_as_float(0x7f800000);
-        int c = 0;
-        if (FILT) {
-          if (RES) { t = tau_l[mt]; c = cnt_l[mt]; }
-          else {
-            if (q < p.nq) t = p.tau[q];
-            c = p.cand_cnt[(int64_t)list * q_total + q];
-          }
-        }
-        bar_wait(bar_accf + 8 * slot, aph);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
-        float rmax = MODE == kModeMax ? rmax_l[mt & 15] : VS_NEG_INF;
-        float va[32], vb[32];
-        constexpr int TN_READ = MODE == kModeNop ? 0 : (MODE == kModeHalf ? TN / 2 : TN);
-        if (TN_READ > 0) tc_ld32(taddr, va);
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN_READ; c0 += 64) {
-          tc_wait_ld();
-          tc_ld32(taddr + (uint32_t)(c0 + 32), vb);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float (&v)[32] = half == 0 ? va : vb;
-            const int cc = c0 + 32 * half;
-            if (half == 1) {
-              tc_wait_ld();
-              if (c0 + 64 < TN_READ) tc_ld32(taddr + (uint32_t)(c0 + 64), va);
-            }
-            if (MODE == kModeDump) {
-              if (q < p.nq) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int64_t r = (int64_t)nt * TN + cc + j;
-                  if (r < p.n_rows) p.dump[(int64_t)q * p.dump_ld + r] = v[j];
-                }
-              }
-            } else {
-              if (l2) {                                  // warp-uniform: key = 2 s - ||x||^2
-                const float4* sq4 = reinterpret_cast<const float4*>(sqb + cc);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 w = sq4[j4];
-                  v[4 * j4 + 0] = fmaf(2.f, v[4 * j4 + 0], -w.x);
-                  v[4 * j4 + 1] = fmaf(2.f, v[4 * j4 + 1], -w.y);
-                  v[4 * j4 + 2] = fmaf(2.f, v[4 * j4 + 2], -w.z);
-                  v[4 * j4 + 3] = fmaf(2.f, v[4 * j4 + 3], -w.w);
-                }
-              }
-              uint32_t mword = 0xffffffffu;              // rows of this chunk that take part
-              if (p.row_mask != nullptr) {
-                const int64_t r0 = (int64_t)nt * TN + cc;
-                mword = r0 < p.n_rows ? __ldg(p.row_mask + (r0 >> 5)) : 0u;
-                if (MODE == kModeMax) {                  // pass 1 bounds the ks-th best TAKING-PART row
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = (mword >> j) & 1u ? v[j] : VS_NEG_INF;
-                }
-              }
-              // maxima of the four 8-column groups (independent 3-input FMNMX trees)
-              float g[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float a = max3(v[8 * u], v[8 * u + 1], v[8 * u + 2]);
-                const float b = max3(v[8 * u + 3], v[8 * u + 4], v[8 * u + 5]);
-                g[u] = max3(a, b, fmaxf(v[8 * u + 6], v[8 * u + 7]));
-              }
-              const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-              if (MODE == kModeMax) rmax = fmaxf(rmax, m);
-              if (FILT && __any_sync(0xffffffffu, m >= t)) {
-                // rare path: take the hits straight from the registers of this chunk (no second
-                // tcgen05.ld).  Per 8-column group one warp-uniform vote; inside, a branch-free hit
-                // mask per lane and a (divergent, almost always single-trip) loop over its set bits
-                // that picks the value with a select chain -- no per-value branches.  Measured at
-                // 10 M x 128, batch 1024 (profiles/r02_k3_probe.txt): 1.96 ms vs 2.14 ms per search
-                // with the first version, which re-read the 8-column groups from TMEM.
-                const int lim = (int)min((int64_t)TN, p.n_rows - (int64_t)nt * TN) - cc;   // live columns
-                const int32_t id0 = (int32_t)((int64_t)nt * TN + cc);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (!__any_sync(0xffffffffu, g[u] >= t)) continue;
-                  uint32_t hits = 0;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) hits |= (v[8 * u + j] >= t ? 1u : 0u) << j;
-                  const int live = lim - 8 * u;                       // columns of this group inside the store
-                  hits &= live >= 8 ? 0xffu : (live <= 0 ? 0u : (1u << live) - 1u);
-                  hits &= mword >> (8 * u);
-                  while (hits) {
-                    const int j = __ffs((int)hits) - 1;
-                    hits &= hits - 1u;
-                    float w = v[8 * u];
-#pragma unroll
-                    for (int jj = 1; jj < 8; ++jj) w = j == jj ? v[8 * u + jj] : w;
-                    if (c < kCandCap) {
-                      p.cand_score[cbase + c] = w;
-                      p.cand_id[cbase + c] = id0 + 8 * u + j;
-                    }
-                    ++c;
-                  }
-                }
-              }
-            }
-          }
-        }
-        // accumulator fully consumed: hand it back to the (leader's) MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2 && crank != 0) bar_arrive_remote(bar_acce + 8 * slot, 0);
-          else bar_arrive(bar_acce + 8 * slot);
-        }
-        if (MODE == kModeMax) {
-          // one maximum per kMaxGroupTiles consecutive tiles of this unit
-          if ((i % p.group_tiles) == p.group_tiles - 1 || i == my_tiles - 1) {
-            p.gmax[(int64_t)q * p.n_groups + uig * p.groups_per_unit + i / p.group_tiles] = rmax;
-            rmax = VS_NEG_INF;
-          }
-          rmax_l[mt & 15] = rmax;
-        }
-        if (FILT) {
-          if (RES) cnt_l[mt] = c;
-          else p.cand_cnt[(int64_t)list * q_total + q] = c;
-        }
-      }
-    }
-    if (MODE == kModeMax) {   // groups this unit has no tiles for
-      for (int g = (my_tiles + p.group_tiles - 1) / p.group_tiles; g < p.groups_per_unit; ++g)
-        for (int mt = grp; mt < m_count; mt += kEpiGroups)
-          p.gmax[(int64_t)(((m_first + mt) * CG + crank) * kTileM + row) * p.n_groups + uig * p.groups_per_unit + g] =
-              VS_NEG_INF;
-    }
-    // move this thread's private candidates into the dense per-query lists
-    if (FILT) {
-      for (int mt = grp; mt < m_count; mt += kEpiGroups) {   // this warp group's query tiles
-        const int q = ((m_first + mt) * CG + crank) * kTileM + row;
-        if (q >= p.nq) continue;
-        const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
-        int c = RES ? cnt_l[mt] : p.cand_cnt[(int64_t)list * q_total + q];
-        if (c > kCandCap) { p.overflow[q] = 1; c = kCandCap; }
-        if (c == 0) continue;
-        const int base = atomicAdd(p.gcount + q, c);
-        if (base + c > kGlobalCap) { p.overflow[q] = 1; continue; }
-        for (int e = 0; e < c; ++e) {
-          p.glist_s[(int64_t)q * kGlobalCap + base + e] = p.cand_score[cbase + e];
-          p.glist_i[(int64_t)q * kGlobalCap + base + e] = p.cand_id[cbase + e];
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (CG == 2) cluster_sync_all();          // the peer's smem / TMEM stay alive until the leader is done
-  if (warp == 2) {
-    tc_fence_after();
-    Ops::dealloc(tmem_base);
-  }
-}
 
 // ------------------------------------------------------------ small helper kernels
 // queries -> bf16 (normalised for cosine), padded to (m_tiles*128, ld16); also the per-query
@@ -745,58 +109,101 @@ __global__ void prep_queries_fp8_kernel(const float* __restrict__ q, int B, int 
     dst[c] = (unsigned char)__nv_cvt_float_to_fp8(c < dim ? src[c] * sc : 0.f, __NV_SATFINITE, __NV_E4M3);
 }
 
-// tau[q] = the ks-th largest of query q's pass-1 group maxima (-inf with fewer than ks groups).
-// One warp per query: the values are staged in shared memory and the answer is built bit by bit
-// on the order-preserving uint32 encoding (32 counting rounds), so the cost does not depend on
-// the data.  Also clears this search's uncertified-query counter.
+// r-th largest (1-based) of n order-encoded values in shared memory, by a bitwise search over the
+// encoding: 32 counting rounds, so the cost does not depend on the data.  Whole warp.
+__device__ __forceinline__ uint32_t warp_rth_largest(const uint32_t* v, int n, int r, int lane) {
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+    for (int i = lane; i < n; i += 32) c += v[i] >= cand;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= r) T = cand;
+  }
+  return T;
+}
+
+// Pass 1 -> the starting threshold and the threshold ladder of every query.  One warp per query.
+//   lvl[q][0] = the ks-th largest of the query's sample maxima: ks distinct rows reach it, so it is a
+//               lower bound of the ks-th best 16-bit key of the whole database (-inf with fewer than ks
+//               maxima).  tau_cur[q] starts there.
+//   lvl[q][1..]: the ceil(ks/2)-th, ceil(ks/4)-th, ... largest sample maximum, up to the largest one
+//               (where pass 2 will have seen ks rows after about 2, 4, ... times the sample), then
+//               equally spaced extrapolated levels (spacing = the mean spacing per halving of the rank
+//               between lvl 0 and lvl 2, shrinking 5 % per level as a Gaussian tail's does).  ANY
+//               ascending values are valid here: a level only ever becomes the threshold after pass 2
+//               has counted ks rows at or above it (gemm_kernel.cuh).
+// Rows past B (padding of the last query tile) get +inf everywhere.  Also clears this search's
+// uncertified-query counter.
 constexpr int kTauWarps = 4;
+constexpr int kTauList = 320;            // sample maxima at or above lvl 0 kept for the ladder (>= kMaxCand)
 __global__ void __launch_bounds__(kTauWarps * 32)
-tau_select_kernel(const float* __restrict__ gmax, int n_groups, int ks, int B, float* __restrict__ tau,
+tau_select_kernel(const float* __restrict__ gmax, int n_groups, int ks, int B, int rows_padded,
+                  uint32_t* __restrict__ tau_cur, float* __restrict__ lvl, int32_t* __restrict__ lvl_cnt,
                   int32_t* __restrict__ bad) {
   extern __shared__ uint32_t tsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0 && bad != nullptr) bad[0] = 0;
   const int b = blockIdx.x * kTauWarps + warp;
-  if (b >= B) return;
-  uint32_t* v = tsm + (size_t)warp * n_groups;
+  if (b >= rows_padded) return;
+  float* lv = lvl + (int64_t)b * kLevels;
+  if (lane < kLevels) lvl_cnt[(int64_t)b * kLevels + lane] = 0;
+  if (b >= B) {
+    if (lane < kLevels) lv[lane] = __int_as_float(0x7f800000);
+    if (lane == 0) tau_cur[b] = 0xff800000u;             // enc_key(+inf)
+    return;
+  }
+  uint32_t* v = tsm + (size_t)warp * (n_groups + kTauList);
+  uint32_t* top = v + n_groups;
   const float* src = gmax + (int64_t)b * n_groups;
   for (int i = lane; i < n_groups; i += 32) v[i] = enc_key(src[i]);
   __syncwarp();
-  uint32_t T = 0;
-  if (n_groups >= ks) {
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = T | (1u << bit);
-      int c = 0;
-      for (int i = lane; i < n_groups; i += 32) c += v[i] >= cand;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= ks) T = cand;
+  float L[kLevels];
+#pragma unroll
+  for (int j = 0; j < kLevels; ++j) L[j] = __int_as_float(0x7f800000);
+  if (n_groups < ks) {
+    L[0] = VS_NEG_INF;
+  } else {
+    const uint32_t T0 = warp_rth_largest(v, n_groups, ks, lane);
+    L[0] = dec_key(T0);
+    // the maxima at or above lvl 0 (ks of them, more with ties), compacted
+    int m = 0;
+    for (int i0 = 0; i0 < n_groups; i0 += 32) {
+      const int i = i0 + lane;
+      const bool keep = i < n_groups && v[i] >= T0;
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      const int pos = m + __popc(bal & ((1u << lane) - 1u));
+      if (keep && pos < kTauList) top[pos] = v[i];
+      m += __popc(bal);
+    }
+    __syncwarp();
+    if (m <= kTauList) {
+      int nl = 1;
+#pragma unroll
+      for (int j = 1; j < kLevels; ++j) {
+        const int rk = (ks + (1 << j) - 1) >> j;          // ceil(ks / 2^j)
+        const int rprev = (ks + (1 << (j - 1)) - 1) >> (j - 1);
+        if (nl == j && rprev > 1) { L[j] = dec_key(warp_rth_largest(top, m, rk, lane)); nl = j + 1; }
+      }
+      // extrapolated levels
+      float d = nl >= 3 ? 0.5f * (L[2] - L[0]) : (nl == 2 ? L[1] - L[0] : 0.f);
+#pragma unroll
+      for (int j = 1; j < kLevels; ++j) {
+        if (j >= nl) {
+          d *= 0.95f;
+          L[j] = d > 0.f ? L[j - 1] + d : __int_as_float(0x7f800000);
+        }
+      }
+#pragma unroll
+      for (int j = 1; j < kLevels; ++j)                   // ascending whatever the data did
+        if (!(L[j] > L[j - 1])) L[j] = __int_as_float(0x7f800000);
     }
   }
-  if (lane == 0) tau[b] = n_groups >= ks ? dec_key(T) : VS_NEG_INF;
-}
-
-// Between the two ranges of pass 2: the survivors of the first range (every row of it at or above
-// tau) are a far larger sample than pass 1's, so their ks-th largest key is a tighter -- and still
-// valid -- lower bound of the ks-th best key overall; the second range filters against it.
-// One warp per query over its dense survivor list.
-__global__ void __launch_bounds__(kTauWarps * 32)
-tau_refine_kernel(const float* __restrict__ glist_s, const int32_t* __restrict__ gcount, int ks, int B,
-                  float* __restrict__ tau) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * kTauWarps + warp;
-  if (b >= B) return;
-  const int n = min(gcount[b], kGlobalCap);
-  if (n < ks) return;
-  const float* v = glist_s + (int64_t)b * kGlobalCap;
-  uint32_t T = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = T | (1u << bit);
-    int c = 0;
-    for (int i = lane; i < n; i += 32) c += enc_key(v[i]) >= cand;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= ks) T = cand;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kLevels; ++j) lv[j] = L[j];
+    tau_cur[b] = enc_key(L[0]);
   }
-  if (lane == 0) tau[b] = fmaxf(tau[b], dec_key(T));
 }
 
 // Candidate selection + K5 + final ordering + certification in ONE launch, one CTA per query.
@@ -813,11 +220,12 @@ tau_refine_kernel(const float* __restrict__ glist_s, const int32_t* __restrict__
 //        euclidean    : key16 = 2 u^.v^ - ||v||^2 = ||u||^2 - d^2 up to E = 2 * that bound (+ the
 //                       fp32 rounding of ||v||^2, ||u||^2 and d^2, folded into slack)
 //                       certified  <=>  d_k^2  <  ||u||^2 - beta - E
-//      beta = the kc-th candidate's 16-bit key, or tau when fewer than kc rows passed the filter
-//      (no row outside the candidate set has a 16-bit key above beta).  Queries that cannot be
+//      beta = the kc-th candidate's 16-bit key, or the final filter threshold (tau_cur) when fewer than
+//      kc rows passed the filter (no row outside the candidate set has a 16-bit key above beta).  Queries that cannot be
 //      certified (or whose candidate buffers overflowed) are appended to bad[1..], bad[0] counts them.
 constexpr int kFinishThreads = 256;
 constexpr int kMaxCand = 256;
+constexpr int kFinishStage = 1024;       // survivors staged in shared memory (the rest is read from global memory)
 
 struct FinishParams {
   const float* q;            // (B, dim) raw queries
@@ -829,7 +237,7 @@ struct FinishParams {
   const float* glist_s;      // (B, kGlobalCap) survivors of the filter: 16-bit keys
   const int32_t* glist_i;    //                 local row ids
   const int32_t* gcount;     // (B,) survivors per query (may exceed kGlobalCap: overflow is set then)
-  const float* tau;
+  const uint32_t* tau_cur;   // (B,) final filter thresholds, order-encoded
   const int32_t* overflow;
   const float* qerr;
   const float* qlen;
@@ -845,23 +253,23 @@ struct FinishParams {
 __global__ void __launch_bounds__(kFinishThreads)
 select_finish_kernel(const FinishParams p) {
   extern __shared__ __align__(16) unsigned char fsm[];
-  uint32_t* sk = reinterpret_cast<uint32_t*>(fsm);                         // encoded 16-bit keys
-  int* si = reinterpret_cast<int*>(sk + kGlobalCap);
-  float4* qs = reinterpret_cast<float4*>(si + kGlobalCap);                 // prepared query, ld floats
+  uint32_t* sk = reinterpret_cast<uint32_t*>(fsm);                         // encoded 16-bit keys (first kFinishStage)
+  float4* qs = reinterpret_cast<float4*>(sk + kFinishStage);               // prepared query, ld floats
   __shared__ float keys[kMaxCand];
   __shared__ int ids[kMaxCand];
   __shared__ int sel[kMaxCand];
   __shared__ int wcount[2][kFinishThreads / 32];
   __shared__ int cnt_hi, cnt_eq, have_sh;
+  __shared__ uint32_t T_sh;
   __shared__ float kth_sh, qsq_sh;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool l2 = p.metric == VS_METRIC_EUCLIDEAN;
   const int n = min(p.gcount[b], kGlobalCap);
-  for (int i = tid; i < n; i += kFinishThreads) {
-    sk[i] = enc_key(p.glist_s[(int64_t)b * kGlobalCap + i]);
-    si[i] = p.glist_i[(int64_t)b * kGlobalCap + i];
-  }
-  if (tid == 0) { cnt_hi = 0; cnt_eq = 0; have_sh = 0; kth_sh = VS_NEG_INF; }
+  const float* gs = p.glist_s + (int64_t)b * kGlobalCap;
+  const int32_t* gi = p.glist_i + (int64_t)b * kGlobalCap;
+  for (int i = tid; i < min(n, kFinishStage); i += kFinishThreads) sk[i] = enc_key(gs[i]);
+  auto key_at = [&](int i) -> uint32_t { return i < kFinishStage ? sk[i] : enc_key(gs[i]); };
+  if (tid == 0) { cnt_hi = 0; cnt_eq = 0; have_sh = 0; kth_sh = VS_NEG_INF; T_sh = 0; }
   const float* src = p.q + (size_t)b * p.dim;
   if (warp == 0) {
     float acc = 0.f;
@@ -876,14 +284,28 @@ select_finish_kernel(const FinishParams p) {
     if (lane == 0) qsq_sh = tot;
   }
   __syncthreads();
-  // ---- 1. the kc best survivors by 16-bit key
+  // ---- 1. the kc best survivors by 16-bit key: sel[0..nsel) = their positions in the survivor list
   const bool full = n >= p.kc;
-  uint32_t T = 0;
-  if (full) {
+  uint32_t T = 0;                                  // full: the kc-th largest key
+  if (!full) {
+    for (int i = tid; i < n; i += kFinishThreads) sel[i] = i;
+  } else if (n <= kFinishThreads) {
+    // the usual case (the adaptive filter passes 100-200 rows): one survivor per thread, ranked by counting
+    if (tid < n) {
+      const uint32_t mk = sk[tid];
+      int r = 0;
+      for (int j = 0; j < n; ++j) { const uint32_t o = sk[j]; r += (o > mk) || (o == mk && j < tid); }
+      if (r < p.kc) sel[r] = tid;
+      if (r == p.kc - 1) T_sh = mk;
+    }
+    __syncthreads();
+    T = T_sh;
+  } else {
+    // bitwise search for the kc-th largest key, then compaction
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t cand = T | (1u << bit);
       int c = 0;
-      for (int i = tid; i < n; i += kFinishThreads) c += sk[i] >= cand;
+      for (int i = tid; i < n; i += kFinishThreads) c += key_at(i) >= cand;
       c = __reduce_add_sync(0xffffffffu, c);
       if (lane == 0) wcount[bit & 1][warp] = c;
       __syncthreads();
@@ -892,31 +314,48 @@ select_finish_kernel(const FinishParams p) {
       for (int w = 0; w < kFinishThreads / 32; ++w) tot += wcount[bit & 1][w];
       if (tot >= p.kc) T = cand;
     }
-  }
-  for (int i = tid; i < n; i += kFinishThreads)
-    if (!full || sk[i] > T) sel[atomicAdd(&cnt_hi, 1)] = i;
-  __syncthreads();
-  if (full) {
-    const int hi = cnt_hi;                       // < kc: fewer than kc keys exceed the kc-th largest
     for (int i = tid; i < n; i += kFinishThreads)
-      if (sk[i] == T) { const int pos = hi + atomicAdd(&cnt_eq, 1); if (pos < p.kc) sel[pos] = i; }
+      if (key_at(i) > T) sel[atomicAdd(&cnt_hi, 1)] = i;
+    __syncthreads();
+    const int hi = cnt_hi;                         // < kc: fewer than kc keys exceed the kc-th largest
+    for (int i = tid; i < n; i += kFinishThreads)
+      if (key_at(i) == T) { const int pos = hi + atomicAdd(&cnt_eq, 1); if (pos < p.kc) sel[pos] = i; }
   }
   __syncthreads();
   const int nsel = full ? p.kc : n;
-  // ---- 2. exact fp32 scores of the candidates
+  // ---- 2. exact fp32 scores of the candidates (K5): four rows in flight per warp, each with K2's
+  //         accumulation order (per-lane fma chain over its float4 columns, then the xor butterfly)
   const int nvec = p.ld >> 2;
-  for (int e = warp; e < nsel; e += kFinishThreads / 32) {
-    const int id = si[sel[e]];
-    const float4* x = reinterpret_cast<const float4*>(p.rows) + (int64_t)id * nvec;
-    float acc = 0.f;
-    if (l2) { for (int c = lane; c < nvec; c += 32) acc = sqdiff4_acc(acc, ldg_stream(x + c), qs[c]); }
-    else { for (int c = lane; c < nvec; c += 32) acc = dot4_acc(acc, ldg_stream(x + c), qs[c]); }
-    const float tot = warp_sum(acc);
-    float key;
-    if (p.metric == VS_METRIC_COSINE) key = tot / __ldg(p.norms + id);
-    else if (l2) key = -sqrtf(tot);
-    else key = tot;
-    if (lane == 0) { keys[e] = key; ids[e] = p.id_map ? p.id_map[id] : id; }
+  constexpr int kWarps = kFinishThreads / 32;
+  for (int e0 = warp; e0 < nsel; e0 += 4 * kWarps) {
+    int id[4];
+    const float4* x[4];
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kWarps;
+      id[u] = e < nsel ? gi[sel[e]] : gi[sel[e0]];
+      x[u] = reinterpret_cast<const float4*>(p.rows) + (int64_t)id[u] * nvec;
+      acc[u] = 0.f;
+    }
+    for (int c = lane; c < nvec; c += 32) {
+      const float4 qv = qs[c];
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = ldg_stream(x[u] + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = l2 ? sqdiff4_acc(acc[u], xv[u], qv) : dot4_acc(acc[u], xv[u], qv);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kWarps;
+      const float tot = warp_sum(acc[u]);
+      float key;
+      if (p.metric == VS_METRIC_COSINE) key = tot / __ldg(p.norms + id[u]);
+      else if (l2) key = -sqrtf(tot);
+      else key = tot;
+      if (lane == 0 && e < nsel) { keys[e] = key; ids[e] = p.id_map ? p.id_map[id[u]] : id[u]; }
+    }
   }
   __syncthreads();
   // ---- 3. rank by counting
@@ -937,7 +376,7 @@ select_finish_kernel(const FinishParams p) {
   // ---- 4. certification
   const float max_err = __uint_as_float(p.bounds[0]);
   const float max_len = __uint_as_float(p.bounds[1]);
-  const float beta = full ? dec_key(T) : p.tau[b];
+  const float beta = full ? dec_key(T) : dec_key(p.tau_cur[b]);
   bool ok = p.overflow[b] == 0;
   if (ok && !(!full && p.n_rows <= p.kc)) {
     const float ql = p.qlen[b];
@@ -953,7 +392,7 @@ select_finish_kernel(const FinishParams p) {
   if (!ok) p.bad[1 + atomicAdd(p.bad, 1)] = b;
 }
 
-__global__ void fill_f32_kernel(float* p, float v, int64_t n) {
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = v;
 }
@@ -1013,14 +452,6 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int
   return VS_OK;
 }
 
-struct GemmPlan {
-  int mt;            // resident query tiles per unit (0 = streaming)
-  int cg;            // CTAs per MMA: 1, or 2 (CTA pairs, cta_group::2)
-  int stages;
-  size_t smem;
-  int tn;            // database rows per tile (MMA N)
-};
-
 // CTAs per MMA.  Measured on B200: CTA pairs win where the kernel streams both
 // operands (K > 256: +9 % at D = 768, +67 % at D = 1536).  With resident queries (K <= 256) one
 // CTA per MMA is faster (profiles/r01_k3_probe_experiments.txt: 2.24 vs 3.29 ms at 10 M x 128):
@@ -1038,7 +469,9 @@ static int gemm_cta_group(int kchunks) {
 static void plan_gemm(int kchunks, int m_tiles, int cg, bool l2, GemmPlan* plan) {
   const size_t sq_res = l2 ? (size_t)kEpiGroupsRes * 2 * kResTN * 4 : 0;
   const size_t sq_str = l2 ? (size_t)kEpiGroupsStream * 2 * 256 * 4 : 0;
-  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/ - (l2 ? std::max(sq_res, sq_str) : 0);
+  // tail of the carve-up: barriers (512 B), the hit queues, euclidean's ||x||^2 buffers
+  const size_t tail_res = 512 + hq_bytes(true) + sq_res, tail_str = 512 + hq_bytes(false) + sq_str;
+  const size_t limit = 227 * 1024 - 1024 /*alignment*/ - std::max(tail_res, tail_str);
   const int um_tiles = m_tiles / cg;
   if (kchunks <= 4) {   // K <= 256: resident queries
     int mt = kchunks <= 2 ? 4 : 1;
@@ -1048,88 +481,61 @@ static void plan_gemm(int kchunks, int m_tiles, int cg, bool l2, GemmPlan* plan)
     const size_t stage = (size_t)kchunks * (kResTN / cg) * 128;  // kResTN / cg database rows per CTA
     int stages = (int)((limit - a) / stage);
     if (stages > 4) stages = 4;
-    if (stages >= 2) { *plan = {mt, cg, stages, a + stages * stage + 1024 + 512 + sq_res, kResTN}; return; }
+    if (stages >= 2) {
+      GemmPlan pl;
+      pl.mt = mt; pl.cg = cg; pl.stages = stages; pl.smem = a + stages * stage + 1024 + tail_res; pl.tn = kResTN;
+      *plan = pl;
+      return;
+    }
   }
-  // streaming: query chunk + this CTA's share of the 256-row database chunk
-  const size_t stage = (size_t)(cg == 2 ? 2 : 3) * kChunkBytes;
-  int stages = (int)(limit / stage);
-  if (stages > 6) stages = 6;
-  *plan = {0, cg, stages, stages * stage + 1024 + 512 + sq_str, 256};
+  // STREAMING: query and database chunks stream through a ring of one-chunk slots (16 KB per CTA
+  // of a pair, 32 KB for a single CTA's 256 database rows): a K step takes a query slot and a
+  // database slot, 12 slots = 6 K steps in flight.  Optional query-group layout (like RESIDENT's):
+  // every unit serves ONE query tile whose first K chunks stay resident next to a 6-slot ring
+  // (D = 768: 8 of 12 chunks, a third less L2 -> SM operand traffic).
+  const size_t slot = (size_t)(cg == 2 ? 1 : 2) * kChunkBytes;
+  const size_t lim = limit;
+  int a_res = 0, m_per_unit = um_tiles;
+  // Measured on the B200 (profiles/r02_k3_probe.txt): with query groups the ring is left with three
+  // K steps in flight and the kernel is SLOWER (1 M x 768: 1.49 vs 1.30 ms, 1 M x 1536: 2.63 vs 2.29 ms),
+  // so one group is the default; B200VS_GEMM_QGROUPS=1 selects the query-group layout.
+  const char* e = getenv("B200VS_GEMM_QGROUPS");
+  if (e && *e == '1') {
+    m_per_unit = 1;
+    a_res = (int)std::min<int64_t>(kchunks, ((int64_t)lim - 6 * (int64_t)slot) / kChunkBytes);
+    if (a_res < 0) a_res = 0;
+  }
+  int stages = (int)((lim - (size_t)a_res * kChunkBytes) / slot);
+  if (stages > 12) stages = 12;
+  GemmPlan pl;
+  pl.a_res_k = a_res; pl.m_per_unit = m_per_unit; pl.mt = 0; pl.cg = cg; pl.stages = stages;
+  pl.smem = (size_t)a_res * kChunkBytes + stages * slot + 1024 + tail_str; pl.tn = 256;
+  *plan = pl;
 }
 
 // rows per TMA box of the database operand: RESIDENT CTAs load 128 / cg rows per tile in one
 // box, STREAMING CTAs 256 / cg rows as one or two boxes of 128
 static int x_box_rows(const GemmPlan& plan) { return plan.mt > 0 ? std::min(128, kResTN / plan.cg) : 128; }
 
-template <int MT, int MODE, int CG>
-static int launch_gemm_tmc(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int grid, size_t smem,
-                           cudaStream_t stream) {
-  auto kern = gemm_topk_kernel<MT, MODE, CG>;
-  VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(gemm_threads(MT > 0));
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  {
-    ProfScope prof(kProfGemm, stream);
-    VS_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, p));
-  }
-  count_launch();
-  VS_CHECK_LAUNCH();
-  return VS_OK;
-}
-
-template <int MT, int MODE>
-static int launch_gemm_tm(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int cg, int grid,
-                          size_t smem, cudaStream_t stream) {
-  return cg == 2 ? launch_gemm_tmc<MT, MODE, 2>(mq, mx, p, grid, smem, stream)
-                 : launch_gemm_tmc<MT, MODE, 1>(mq, mx, p, grid, smem, stream);
-}
-
-template <int MT>
-static int launch_gemm_t(const CUtensorMap& mq, const CUtensorMap& mx, const GemmParams& p, int cg, int grid,
-                         size_t smem, cudaStream_t stream) {
-  switch (p.mode) {
-    case kModeFilter: return launch_gemm_tm<MT, kModeFilter>(mq, mx, p, cg, grid, smem, stream);
-    case kModeMax: return launch_gemm_tm<MT, kModeMax>(mq, mx, p, cg, grid, smem, stream);
-#ifdef VS_GEMM_DEBUG_MODES
-    case kModeNop: return launch_gemm_tm<MT, kModeNop>(mq, mx, p, cg, grid, smem, stream);
-    case kModeHalf: return launch_gemm_tm<MT, kModeHalf>(mq, mx, p, cg, grid, smem, stream);
-#endif
-    default: return launch_gemm_tm<MT, kModeDump>(mq, mx, p, cg, grid, smem, stream);
-  }
-}
-
 // units (CTAs or CTA pairs) a launch uses, its query groups and candidate lists per query
 static void gemm_units(const GemmPlan& plan, int m_tiles, int n_tiles, int num_sms, int* units_out, int* ngroups_out,
                        int* lists_out) {
   int units = num_sms / plan.cg;
-  int ngroups = 1, lists;
-  if (plan.mt > 0) {
-    const int um_tiles = m_tiles / plan.cg;
-    ngroups = (um_tiles + plan.mt - 1) / plan.mt;
-    const int64_t want = (int64_t)n_tiles * ngroups;
-    if (want < units) units = (int)want;
-    if (units < ngroups) units = ngroups;
-    lists = (units + ngroups - 1) / ngroups;
-  } else {
-    if (n_tiles < units) units = n_tiles;
-    lists = units;
-  }
+  const int um_tiles = m_tiles / plan.cg;
+  const int span = plan.mt > 0 ? plan.mt : plan.m_per_unit;      // query tiles per group
+  const int ngroups = (um_tiles + span - 1) / span;
+  const int64_t want = (int64_t)n_tiles * ngroups;
+  if (want < units) units = (int)want;
+  if (units < ngroups) units = ngroups;
+  const int lists = (units + ngroups - 1) / ngroups;
   *units_out = units; *ngroups_out = ngroups; *lists_out = lists;
 }
 
 static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtensorMap& mx, GemmParams p,
                        int num_sms, int* lists_out, cudaStream_t stream) {
   p.stages = plan.stages;
+  p.a_res_k = plan.a_res_k;
+  p.m_per_unit = plan.m_per_unit > 0 ? plan.m_per_unit : 1;
   if (p.tile_stride < 1) p.tile_stride = 1;
   p.idesc = instr_desc(kTileM * plan.cg, plan.tn, p.fp16 ? 0 : 1);
   int units, lists;
@@ -1141,14 +547,15 @@ static int launch_gemm(const GemmPlan& plan, const CUtensorMap& mq, const CUtens
     p.n_groups = lists * p.groups_per_unit;
   }
   const int grid = units * plan.cg;
-  switch (plan.mt) {
-    case 0: return launch_gemm_t<0>(mq, mx, p, plan.cg, grid, plan.smem, stream);
-    case 1: return launch_gemm_t<1>(mq, mx, p, plan.cg, grid, plan.smem, stream);
-    case 2: return launch_gemm_t<2>(mq, mx, p, plan.cg, grid, plan.smem, stream);
-    case 4: return launch_gemm_t<4>(mq, mx, p, plan.cg, grid, plan.smem, stream);
-  }
-  set_error("internal: bad GEMM plan");
-  return VS_ERR_INVALID;
+  if (g_trace == 1)
+    fprintf(stderr, "[b200vs trace] gemm mode %d nq %d m_tiles %d n_tiles %d first %d stride %d kch %d mt %d cg %d stages %d "
+            "a_res %d m_per_unit %d ngroups %d lists %d grid %d smem %zu n_groups %d gpu %d gt %d l2 %d mask %d\n",
+            p.mode, p.nq, p.m_tiles, p.n_tiles, p.tile_first, p.tile_stride, p.kchunks, plan.mt, plan.cg, p.stages,
+            p.a_res_k, p.m_per_unit, p.ngroups, lists, grid, plan.smem, p.n_groups, p.groups_per_unit, p.group_tiles,
+            p.sqnorms != nullptr, p.row_mask != nullptr);
+  // the general-key kernels only where they are needed: the plain ones carry no trace of them
+  if (p.sqnorms != nullptr || p.row_mask != nullptr) return launch_gemm_general(plan, mq, mx, p, grid, stream);
+  return launch_gemm_plain(plan, mq, mx, p, grid, stream);
 }
 
 static int gemm_enabled() {
@@ -1169,34 +576,90 @@ static int gemm_min_batch(const vs_store* s) {
 }
 
 // candidates kept for rescoring
-static int cand_count(int kk) { return std::max(2 * kk, kk + 22); }
+// Candidates kept for the exact rescoring: the certification margin is the gap between the k-th and
+// the kc-th best row.  Cosine keys are fp16 of unit vectors (error ~4e-4 against gaps of 1e-2..1e-3):
+// 2k is enough.  Euclidean / dot_product keys carry the bf16 rounding of un-normalised rows (config C,
+// 1 M x 1536 top-100: E ~ 17 in squared distance against a rank-100 to rank-200 gap of ~20, which
+// failed for 60 % of the queries and cost a second GEMM pass): 2.5k there, capped by kMaxCand.
+static int cand_count(const vs_store* s, int kk) {
+  const int base = std::max(2 * kk, kk + 22);
+  if (s->metric == VS_METRIC_COSINE || base > kMaxCand) return base;
+  return std::min(kMaxCand, std::max(5 * kk / 2, kk + 22));
+}
 // rows the pass-1 threshold is guaranteed to admit (see gemm_block)
 static int sample_rank(int kk) { return kk + std::max(6, kk / 2); }
 
 bool gemm_supported(const vs_store* s, int64_t n, int B, int kk) {
   if (!gemm_enabled() || !s->shadow) return false;
   if (B < gemm_min_batch(s) || s->dim > 8192) return false;
-  if (cand_count(kk) > kMaxCand) return false;            // k <= 128
+  if (cand_count(s, kk) > kMaxCand) return false;            // k <= 128
   if (n < 65536) return false;                              // small stores: the scan is enough
   return true;
 }
 
+// The workspace of one enqueue: one recycled device block carved into 1 KB-aligned pieces.
+// Blocks live in the store (vs_store::ws_blocks), not in the stream-ordered allocator: with two
+// searches in flight on two streams the allocator either serialises the streams (a block freed on
+// one stream is reused on the other behind an internal dependency) or allocates afresh per search.
 struct Ws {
   std::vector<std::pair<void**, size_t>> items;
-  unsigned char* base = nullptr;
+  vs_store* store = nullptr;
+  int block = -1;
   cudaStream_t stream = nullptr;
   template <typename T> void want(T** slot, size_t count) { items.push_back({(void**)slot, count * sizeof(T)}); }
-  int alloc(cudaStream_t st) {
+  int alloc(vs_store* s, cudaStream_t st) {
+    store = s;
     stream = st;
     size_t total = 0;
     for (auto& it : items) total += (size_t)round_up((int64_t)it.second, 1024);
-    VS_CUDA(cudaMallocAsync((void**)&base, total ? total : 1024, st));
+    if (total == 0) total = 1024;
+    {
+      std::lock_guard<std::mutex> g(s->ws_mu);
+      int pick = -1;
+      for (int pass = 0; pass < 2 && pick < 0; ++pass)
+        for (size_t i = 0; i < s->ws_blocks.size() && pick < 0; ++i) {
+          auto& b = s->ws_blocks[i];
+          if (b.busy || b.bytes < total) continue;
+          // pass 0: last used on this stream; pass 1: its last use on another stream has completed
+          if (pass == 0 ? b.stream == st : cudaEventQuery(b.ev) == cudaSuccess) pick = (int)i;
+        }
+      cudaGetLastError();                       // cudaErrorNotReady from the queries above
+      if (pick < 0) {
+        vs_store::WsBlock b;
+        // (a block too small for this search stays in the list for smaller ones; the list is short:
+        //  one or two blocks per stream in flight and per size class reached)
+        const size_t bytes = (size_t)round_up((int64_t)total + total / 8, 1 << 20);
+        VS_CUDA(cudaMalloc(&b.ptr, bytes));
+        b.bytes = bytes;
+        VS_CUDA(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
+        s->ws_blocks.push_back(b);
+        pick = (int)s->ws_blocks.size() - 1;
+      }
+      s->ws_blocks[pick].busy = true;
+      block = pick;
+    }
+    unsigned char* base = (unsigned char*)s->ws_blocks[block].ptr;
     size_t off = 0;
     for (auto& it : items) { *it.first = base + off; off += (size_t)round_up((int64_t)it.second, 1024); }
     return VS_OK;
   }
-  ~Ws() { if (base) cudaFreeAsync(base, stream); }
+  // everything that uses the block has been enqueued on `stream`
+  ~Ws() {
+    if (block < 0) return;
+    std::lock_guard<std::mutex> g(store->ws_mu);
+    auto& b = store->ws_blocks[block];
+    cudaEventRecord(b.ev, stream);
+    b.stream = stream;
+    b.busy = false;
+  }
 };
+void free_ws_blocks(vs_store* s) {
+  for (auto& b : s->ws_blocks) {
+    if (b.ev) cudaEventDestroy(b.ev);
+    if (b.ptr) cudaFree(b.ptr);
+  }
+  s->ws_blocks.clear();
+}
 
 // exact fp32 scan of selected queries (defined in search.cu)
 int scan_queries_exact(vs_store* s, int64_t n, const float* q, int B, int kk, bool use_tma, const uint32_t* row_mask,
@@ -1249,45 +712,43 @@ static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int
   const int cg = gemm_cta_group(kch);
   const int m_tiles = ((B + kTileM * cg - 1) / (kTileM * cg)) * cg;     // a multiple of cg
   const int rows_padded = m_tiles * kTileM;
-  const int kc = (int)std::min<int64_t>(kc_want > 0 ? kc_want : cand_count(kk), n);
+  const int kc = (int)std::min<int64_t>(kc_want > 0 ? kc_want : cand_count(s, kk), n);
   GemmPlan plan;
   plan_gemm(kch, m_tiles, cg, l2, &plan);
   const int tn = plan.tn;
   const int n_tiles = (int)((n + tn - 1) / tn);
-  // pass-1 sample.  tau[q] = the ks-th largest per-group maximum of the sample: ks distinct rows
-  // reach it, so it is a lower bound of the ks-th best 16-bit key of the whole database.  ks only
-  // has to exceed k by a margin (the filter may pass FEWER than kc rows: then no row outside the
-  // candidate set exceeds tau and the certification uses beta = tau); a wide retry (kc_want > 0)
-  // asks for all of its kc candidates.  The filter passes about ks / f rows per query, i.e. a
-  // fraction 1024 ks / (f N) of the 32 x 32 epilogue chunks take the rare path (~r chunk times
-  // each), while pass 1 costs ~0.8 f of a full pass: minimising 0.8 f + r 1024 ks / (f N) gives
-  // f = sqrt(1280 r ks / N); r ~ 0.6 for the register-based rare path (tuned on the B200,
-  // profiles/r02_k3_probe.txt).  At least 4 ks groups, at most 4096 (K4's capacity), whole tiles.
+  // Pass 1 (the kernel in MAX mode over a sample of the tiles, spread over the whole row range)
+  // only SEEDS the filter: tau_select turns the per-tile maxima of the sample into a starting
+  // threshold (the ks-th largest maximum: ks distinct rows reach it, so it is a lower bound of the
+  // ks-th best 16-bit key of the database) and a ladder of higher trial thresholds that pass 2
+  // climbs as soon as it has itself counted ks rows at a level.  The filter therefore passes about
+  // ks (log2(1 / f) + 1) rows per query however small the sample fraction f is, and the sample can
+  // be small: eight tiles per unit (measured on the B200, profiles/r02_k3_probe.txt: 10 M x 128 is
+  // fastest with ~800 sample tiles = 1 %, a 1.25 M-row shard with ~600 = 6 %; fewer tiles leave the
+  // ladder's first levels too low, more cost pass-1 time), at least 4 ks tiles.  ks only has to exceed k by a margin (the filter may pass FEWER than kc rows: then
+  // no row outside the candidate set exceeds the final threshold and the certification uses that);
+  // a wide retry (kc_want > 0) asks for all of its kc candidates.
   // With a row mask only n_live rows take part: the sample must hold enough of THOSE.
   int ks = kc_want > 0 ? kc : std::min(kc, sample_rank(kk));
   if (const char* e = getenv("B200VS_GEMM_KS")) { if (*e) ks = std::max(1, std::min(kc, atoi(e))); }   // diagnostic
   const double live_frac = std::max(1e-9, std::min(1.0, (double)n_live / (double)n));
-  double f = std::sqrt(768.0 * ks / ((double)n * live_frac)) ;
-  // K > 256 (STREAMING): the MMAs of a tile take several times longer than its epilogue, so the
-  // rare path is hidden and the sample only has to keep the survivors (about 1.2 ks / f per
-  // query) within the candidate buffers (64 per CTA pair and query) and K4's capacity.
-  if (kch > 4) f = std::min(f, ks / (750.0 * live_frac));
-  if (const char* e = getenv("B200VS_GEMM_SAMPLE")) { if (*e) f = atof(e); }   // diagnostic override
-  if (f > 0.5) f = 0.5;
-  if (f < 1.0 / 128) f = 1.0 / 128;
   const int full_tiles = (int)(n / tn);
-  int s_tiles = (int)std::min<int64_t>(std::max<int64_t>((int64_t)(f * (double)n) / tn, (int64_t)(4 * ks / live_frac)),
-                                       4096 * kMaxGroupTiles);
-  if (s_tiles > full_tiles) s_tiles = full_tiles;
-  // the sample is spread over the whole row range (every `s_stride`-th tile), not a prefix: on a
-  // time-ordered or clustered ingest a prefix can be unlike the rest and give a useless threshold
+  int f_units, f_ngroups, f_lists;
+  gemm_units(plan, m_tiles, n_tiles, s->num_sms, &f_units, &f_ngroups, &f_lists);
+  int64_t want_tiles = std::max<int64_t>((int64_t)(4 * ks / live_frac), 8 * (int64_t)f_lists);
+  if (const char* e = getenv("B200VS_GEMM_SAMPLE")) { if (*e) want_tiles = (int64_t)(atof(e) * (double)n / tn); }   // diagnostic
+  // at most 4096 maxima per query (tau_select's shared memory), counted in whole rounds of the units
+  int s_tiles = (int)std::min<int64_t>(want_tiles, full_tiles);
+  if (s_tiles > 4096 / f_lists * f_lists) s_tiles = 4096 / f_lists * f_lists;
+  // every `s_stride`-th tile, not a prefix: on a time-ordered or clustered ingest a prefix can be
+  // unlike the rest and give a useless starting threshold
   const int s_stride = s_tiles > 0 ? std::max(1, full_tiles / s_tiles) : 1;
   int s_units, s_ngroups, s_lists;
   gemm_units(plan, m_tiles, s_tiles, s->num_sms, &s_units, &s_ngroups, &s_lists);
-  const int gt = s_tiles / kMaxGroupTiles >= 4 * ks ? kMaxGroupTiles : 1;
-  const int s_groups = s_lists * (((s_tiles + s_lists - 1) / s_lists + gt - 1) / gt);
-  const bool sampled = s_tiles / gt >= 2 * ks && s_groups <= 4096 && live_frac >= 0.2;
-  // Too few rows for a useful threshold (fewer than 2 ks sample groups, or a filter that leaves
+  const int gt = 1;                                     // one maximum per sample tile
+  const int s_groups = s_lists * ((s_tiles + s_lists - 1) / s_lists);
+  const bool sampled = s_tiles >= 2 * ks && s_groups <= 4096 && live_frac >= 0.2;
+  // Too few rows for a useful threshold (fewer than 2 ks sample tiles, or a filter that leaves
   // less than a fifth of the rows): every row would be a candidate and the per-thread buffers
   // would overflow.  The exact scan serves such a search directly (for the uncertified modes
   // too: its recall is 1).
@@ -1306,11 +767,14 @@ static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int
 
   const int max_lists = s->num_sms;
   Ws ws;
-  __nv_bfloat16* qb; float *qerr, *qlen, *tau, *gmax, *cs, *gls; int32_t *ci, *ccnt, *ovf, *gli, *gcnt;
+  __nv_bfloat16* qb; float *qerr, *qlen, *lvl, *gmax, *cs, *gls; int32_t *ci, *ccnt, *ovf, *gli, *gcnt, *lcnt;
+  uint32_t* tau;
   ws.want(&qb, (size_t)rows_padded * K);
   ws.want(&qerr, (size_t)rows_padded);
   ws.want(&qlen, (size_t)rows_padded);
   ws.want(&tau, (size_t)rows_padded);
+  ws.want(&lvl, (size_t)rows_padded * kLevels);
+  ws.want(&lcnt, (size_t)rows_padded * kLevels);
   ws.want(&gmax, (size_t)rows_padded * s_groups);
   ws.want(&cs, (size_t)max_lists * rows_padded * kCandCap);
   ws.want(&ci, (size_t)max_lists * rows_padded * kCandCap);
@@ -1319,7 +783,7 @@ static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int
   ws.want(&gli, (size_t)rows_padded * kGlobalCap);
   ws.want(&ovf, (size_t)rows_padded);      // cleared by the prep kernel, like gcnt
   ws.want(&gcnt, (size_t)rows_padded);
-  if (int rc = ws.alloc(stream)) return rc;
+  if (int rc = ws.alloc(s, stream)) return rc;
 
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
@@ -1338,46 +802,49 @@ static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int
 
   GemmParams p = {};
   p.kchunks = kch; p.n_rows = n; p.m_tiles = m_tiles; p.nq = B; p.fp16 = (fp16 || fp8) ? 1 : 0; p.fp8 = fp8 ? 1 : 0;
-  p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf; p.tau = tau;
+  p.cand_score = cs; p.cand_id = ci; p.cand_cnt = ccnt; p.overflow = ovf;
+  // Rows that must reach a ladder level before it becomes the threshold.  The final threshold then
+  // sits near the adapt_rank-th best key, and the certification margin is the gap between the k-th
+  // and about the adapt_rank-th best row: ks is enough where the 16-bit error E is small against the
+  // spacing of the top scores (cosine: fp16 of unit vectors); euclidean / dot_product keys carry
+  // bf16 rounding of un-normalised rows (config C: E ~ 17 against a rank-100 to rank-150 gap of ~11),
+  // so there the ladder stops at the kc-th best and beta is the kc-th candidate as before.
+  p.tau_cur = tau; p.lvl = lvl; p.lvl_cnt = lcnt;
+  p.adapt_rank = s->metric == VS_METRIC_COSINE ? ks : kc;
+  if (const char* e = getenv("B200VS_GEMM_RANK")) {      // diagnostic: ks | kc | a number
+    if (!strcmp(e, "ks")) p.adapt_rank = ks; else if (!strcmp(e, "kc")) p.adapt_rank = kc; else if (*e) p.adapt_rank = std::max(1, atoi(e));
+  }
+  if (const char* e = getenv("B200VS_GEMM_ADAPT")) { if (*e == '0') p.adapt_rank = 1 << 30; }   // diagnostic: fixed threshold
   p.glist_s = gls; p.glist_i = gli; p.gcount = gcnt;
   p.sqnorms = l2 ? (const float*)s->sqnorms.ptr() : nullptr;
   p.row_mask = row_mask;
 
   if (plan.mt == 0)   // STREAMING keeps its running candidate counts in global memory
     VS_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)max_lists * rows_padded * 4, stream));
-  // pass 1: per-query maxima of the sample tiles -> tau = ks-th largest
+  // pass 1: per-query maxima of the sample tiles -> starting threshold + ladder
   p.mode = kModeMax; p.n_tiles = s_tiles; p.tile_stride = s_stride; p.gmax = gmax; p.group_tiles = gt;
   if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
-  tau_select_kernel<<<(B + kTauWarps - 1) / kTauWarps, kTauWarps * 32, (size_t)kTauWarps * s_groups * 4, stream>>>(
-      gmax, s_groups, ks, B, tau, bad);
+  {
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(tau_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
+    tau_select_kernel<<<(rows_padded + kTauWarps - 1) / kTauWarps, kTauWarps * 32,
+                        (size_t)kTauWarps * (s_groups + kTauList) * 4, stream>>>(gmax, s_groups, ks, B, rows_padded, tau,
+                                                                                 lvl, lcnt, bad);
+  }
   count_launch();
   VS_CHECK_LAUNCH();
   // diagnostic (timing only, results are wrong): no row passes the filter, so pass 2 never
   // takes its rare path
   if (const char* e = getenv("B200VS_GEMM_TAU_INF")) {
-    if (*e == '1') fill_f32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, __builtin_inff(), rows_padded);
+    if (*e == '1') fill_u32_kernel<<<(rows_padded + 255) / 256, 256, 0, stream>>>(tau, 0xff800000u, rows_padded);
   }
   // pass 2: threshold filter over all rows
   p.mode = kModeFilter; p.n_tiles = n_tiles; p.tile_stride = 1; p.gmax = nullptr;
 #ifdef VS_GEMM_DEBUG_MODES
   if (const char* e = getenv("B200VS_GEMM_DBGMODE")) { if (*e == '3' || *e == '4') p.mode = atoi(e); }
 #endif
-  // RESIDENT kernels on a large store run pass 2 as two ranges: a head of ~15 % of the tiles
-  // filtered against pass 1's threshold, tau_refine (the head's survivors are a 4x larger sample
-  // than pass 1's), then the rest against the tighter threshold -- the rare path of the epilogue
-  // fires ~3x less often overall (profiles/r02_k3_probe.txt).  Survivors of both ranges land in the
-  // same dense per-query lists; every row at or above the FINAL tau is among them.
-  int head_tiles = 0;
-  if (plan.mt > 0 && n_tiles >= 16384) head_tiles = (int)(0.15 * n_tiles);
-  if (const char* e = getenv("B200VS_GEMM_HEAD")) { if (*e) head_tiles = (int)(atof(e) * n_tiles); }   // diagnostic
-  if (head_tiles > 0 && head_tiles < n_tiles) {
-    p.n_tiles = head_tiles;
-    if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
-    tau_refine_kernel<<<(B + kTauWarps - 1) / kTauWarps, kTauWarps * 32, 0, stream>>>(gls, gcnt, ks, B, tau);
-    count_launch();
-    VS_CHECK_LAUNCH();
-    p.tile_first = head_tiles; p.n_tiles = n_tiles - head_tiles;
-  }
   if (int rc = launch_gemm(plan, mq, mx, p, s->num_sms, nullptr, stream)) return rc;
   // candidate selection + K5 + final ordering + certification, one CTA per query
   {
@@ -1385,13 +852,13 @@ static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int
     f.q = q; f.dim = s->dim; f.ld = s->ld; f.metric = s->metric; f.B = B; f.k = kk; f.kc = kc; f.n_rows = n;
     f.rows = (const float*)s->rows.ptr(); f.norms = (const float*)s->norms.ptr(); f.id_map = s->id_map();
     f.glist_s = gls; f.glist_i = gli; f.gcount = gcnt;
-    f.tau = tau; f.overflow = ovf; f.qerr = qerr; f.qlen = qlen; f.bounds = s->bounds;
+    f.tau_cur = tau; f.overflow = ovf; f.qerr = qerr; f.qlen = qlen; f.bounds = s->bounds;
     // fp32 accumulation error of the tensor core and of the exact kernels, relative to ||u|| ||v||
     // (tests/test_gemm_gpu.py measures the tensor core's share against float64)
     f.slack = (l2 ? 8.f : 4.f) * (float)s->dim * 5.9604645e-8f + 1e-6f;
     f.certify = certify ? 1 : 0;
     f.out_s = out_scores; f.out_i = out_ids; f.out_stride = out_stride; f.bad = bad;
-    const size_t smem = (size_t)kGlobalCap * 8 + (size_t)s->ld * 4;
+    const size_t smem = (size_t)kFinishStage * 4 + (size_t)s->ld * 4;
     static std::once_flag once;
     std::call_once(once, [] {
       cudaFuncSetAttribute(select_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1435,7 +902,7 @@ static int gemm_block_complete(vs_store* s, const PendingBlock& pb, cudaStream_t
   count_launch();
   VS_CHECK_LAUNCH();
   int rc;
-  const int kc = (int)std::min<int64_t>(cand_count(kk), pb.n);
+  const int kc = (int)std::min<int64_t>(cand_count(s, kk), pb.n);
   const int kc_retry = std::min(4 * kc, kMaxCand);
   if (pb.kc_want == 0 && kc_retry > kc && (int64_t)kc_retry * 8 <= pb.n) {
     s->retries.fetch_add(h_bad);
@@ -1465,9 +932,9 @@ int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certif
     if (!s->shadow8) { set_error("store was created without an fp8 shadow copy (VS_SHADOW_FP8)"); return VS_ERR_STATE; }
     certify = false;            // e4m3 rounding is far above any top-k margin: recall-reported variant
   } else if (!s->shadow) { set_error("store was created without a 16-bit shadow copy"); return VS_ERR_STATE; }
-  if (cand_count(kk) > kMaxCand) { set_error("invalid argument: k too large for the GEMM path (k <= 128)"); return VS_ERR_INVALID; }
+  if (cand_count(s, kk) > kMaxCand) { set_error("invalid argument: k too large for the GEMM path (k <= 128)"); return VS_ERR_INVALID; }
   // the fp8 variant keeps 4x the candidates for the exact rescoring
-  const int kc_want = fp8 ? std::min(4 * cand_count(kk), kMaxCand) : 0;
+  const int kc_want = fp8 ? std::min(4 * cand_count(s, kk), kMaxCand) : 0;
   for (int b0 = 0; b0 < B; b0 += kMaxQueriesPerLaunch) {
     const int nb = std::min(kMaxQueriesPerLaunch, B - b0);
     PendingBlock pb;
@@ -1506,7 +973,7 @@ int gemm_dump_scores(vs_store* s, int64_t n, const float* q, int B, float* out, 
   ws.want(&qb, (size_t)rows_padded * K);
   ws.want(&qerr, (size_t)rows_padded);
   ws.want(&qlen, (size_t)rows_padded);
-  if (int rc = ws.alloc(stream)) return rc;
+  if (int rc = ws.alloc(s, stream)) return rc;
   CUtensorMap mq, mx;
   const bool fp16 = s->metric == VS_METRIC_COSINE;
   if (int rc = make_map(&mq, qb, rows_padded, K, fp16 ? 1 : 0)) return rc;

@@ -46,5 +46,6 @@ int gemm_path(vs_store* s, int64_t n, const float* q, int B, int kk, bool certif
               cudaStream_t stream, vs_ticket* ticket);
 int gemm_complete(vs_store* s, vs_ticket* ticket);
 void free_cert_slots(vs_store* s);
+void free_ws_blocks(vs_store* s);
 
 }  // namespace vs

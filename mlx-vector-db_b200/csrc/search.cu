@@ -246,6 +246,12 @@ int vs_rescore(vs_store* s, const float* q, int B, const int32_t* cand_ids, int 
   return rescore_path(s, q, B, cand_ids, kc, std::min(k, kc), out_scores, out_ids, k, stream);
 }
 
+static bool host_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int vs_search_host(vs_store* s, const float* q_host, int B, int k, int flags,
                    const uint32_t* row_mask_dev, int64_t mask_live, float* out_scores_host, int32_t* out_ids_host) {
   VS_REQUIRE(s != nullptr, "store is NULL");
@@ -262,26 +268,43 @@ int vs_search_host(vs_store* s, const float* q_host, int B, int k, int flags,
   ws.want(&ds, (size_t)B * k);
   ws.want(&di, (size_t)B * k);
   if (int rc = ws.alloc(stream)) return rc;
-  // small transfers go through the store's pinned staging buffers (true async copies)
-  const bool staged = qbytes <= s->pinned_bytes && 2 * obytes <= s->pinned_bytes;
-  if (staged) {
+  // Page-locked caller buffers are copied from / to directly; pageable ones go through the store's
+  // pinned staging buffers when they fit (true async copies), else through the driver's staging.
+  const bool q_direct = host_pinned(q_host) || qbytes > s->pinned_bytes;
+  const bool o_direct = (host_pinned(out_scores_host) && host_pinned(out_ids_host)) || 2 * obytes > s->pinned_bytes;
+  if (q_direct) {
+    VS_CUDA(cudaMemcpyAsync(dq, q_host, qbytes, cudaMemcpyHostToDevice, stream));
+  } else {
     memcpy(s->pinned_in, q_host, qbytes);
     VS_CUDA(cudaMemcpyAsync(dq, s->pinned_in, qbytes, cudaMemcpyHostToDevice, stream));
-  } else {
-    VS_CUDA(cudaMemcpyAsync(dq, q_host, qbytes, cudaMemcpyHostToDevice, stream));
   }
-  if (int rc = vs_search(s, dq, B, k, flags, row_mask_dev, mask_live, ds, di, stream)) return rc;
-  if (staged) {
-    unsigned char* po = (unsigned char*)s->pinned_out;
-    VS_CUDA(cudaMemcpyAsync(po, ds, obytes, cudaMemcpyDeviceToHost, stream));
-    VS_CUDA(cudaMemcpyAsync(po + obytes, di, obytes, cudaMemcpyDeviceToHost, stream));
-    VS_CUDA(cudaStreamSynchronize(stream));
+  // The whole search and the copies back are enqueued before the host waits for anything: the
+  // certification count is checked AFTER the copies are in flight, and only a search that had to
+  // re-run queries (rare) copies its results a second time.
+  vs_ticket ticket;
+  ticket.stream = stream;
+  unsigned char* po = (unsigned char*)s->pinned_out;
+  auto copy_back = [&]() -> int {
+    if (o_direct) {
+      VS_CUDA(cudaMemcpyAsync(out_scores_host, ds, obytes, cudaMemcpyDeviceToHost, stream));
+      VS_CUDA(cudaMemcpyAsync(out_ids_host, di, obytes, cudaMemcpyDeviceToHost, stream));
+    } else {
+      VS_CUDA(cudaMemcpyAsync(po, ds, obytes, cudaMemcpyDeviceToHost, stream));
+      VS_CUDA(cudaMemcpyAsync(po + obytes, di, obytes, cudaMemcpyDeviceToHost, stream));
+    }
+    return VS_OK;
+  };
+  int rc = search_impl(s, dq, B, k, flags, row_mask_dev, mask_live, ds, di, stream, &ticket);
+  if (!rc) rc = copy_back();
+  const int64_t redo0 = s->retries.load() + s->fallbacks.load();
+  const int rc2 = gemm_complete(s, &ticket);          // waits for the certification counts (if any)
+  if (!rc) rc = rc2;
+  if (!rc && s->retries.load() + s->fallbacks.load() != redo0) rc = copy_back();
+  if (rc) { cudaStreamSynchronize(stream); return rc; }
+  VS_CUDA(cudaStreamSynchronize(stream));
+  if (!o_direct) {
     memcpy(out_scores_host, po, obytes);
     memcpy(out_ids_host, po + obytes, obytes);
-  } else {
-    VS_CUDA(cudaMemcpyAsync(out_scores_host, ds, obytes, cudaMemcpyDeviceToHost, stream));
-    VS_CUDA(cudaMemcpyAsync(out_ids_host, di, obytes, cudaMemcpyDeviceToHost, stream));
-    VS_CUDA(cudaStreamSynchronize(stream));
   }
   return VS_OK;
 }

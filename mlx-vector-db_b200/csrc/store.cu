@@ -12,6 +12,17 @@ namespace vs {
 // ------------------------------------------------------------------ errors
 static thread_local std::string t_error;
 std::atomic<int64_t> g_launches{0};
+int g_trace = -1;
+void trace_launch(const char* file, int line) {
+  if (g_trace < 0) { const char* e = getenv("B200VS_TRACE"); g_trace = (e && *e == '1') ? 1 : 0; }
+  if (g_trace == 0) return;
+  const char* base = strrchr(file, '/');
+  fprintf(stderr, "[b200vs trace] launch #%lld at %s:%d ...", (long long)g_launches.load(), base ? base + 1 : file, line);
+  fflush(stderr);
+  const cudaError_t e = cudaDeviceSynchronize();
+  fprintf(stderr, " %s\n", e == cudaSuccess ? "done" : cudaGetErrorString(e));
+  fflush(stderr);
+}
 
 void set_error(const std::string& msg) { t_error = msg; }
 
@@ -222,65 +233,108 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool fp16, float& r
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Fast path for rows of at most 128 floats (one float4 per lane): R rows per warp iteration are
-// loaded together (latency hiding) and stay in registers for the norm, the copy and the shadow.
-constexpr int kAppendR = 4;
+// 16-bit shadow of 8 consecutive prepared components (fp16 for cosine, bf16 otherwise) + the
+// squared rounding error and squared length of the rounded values
+__device__ __forceinline__ uint4 shadow8(const float4& a, const float4& b, bool fp16, float& e2, float& s2) {
+  float q0, q1, q2, q3, q4, q5, q6, q7, t;
+  uint4 o;
+  o.x = pack16(a.x, a.y, fp16, q0, q1);
+  o.y = pack16(a.z, a.w, fp16, q2, q3);
+  o.z = pack16(b.x, b.y, fp16, q4, q5);
+  o.w = pack16(b.z, b.w, fp16, q6, q7);
+  t = a.x - q0; e2 = fmaf(t, t, e2); s2 = fmaf(q0, q0, s2);
+  t = a.y - q1; e2 = fmaf(t, t, e2); s2 = fmaf(q1, q1, s2);
+  t = a.z - q2; e2 = fmaf(t, t, e2); s2 = fmaf(q2, q2, s2);
+  t = a.w - q3; e2 = fmaf(t, t, e2); s2 = fmaf(q3, q3, s2);
+  t = b.x - q4; e2 = fmaf(t, t, e2); s2 = fmaf(q4, q4, s2);
+  t = b.y - q5; e2 = fmaf(t, t, e2); s2 = fmaf(q5, q5, s2);
+  t = b.z - q6; e2 = fmaf(t, t, e2); s2 = fmaf(q6, q6, s2);
+  t = b.w - q7; e2 = fmaf(t, t, e2); s2 = fmaf(q7, q7, s2);
+  return o;
+}
+__device__ __forceinline__ float4 scale4(const float4& v, float r) { return make_float4(v.x * r, v.y * r, v.z * r, v.w * r); }
+
+// Rows are read ONCE into registers (no second pass for the shadow) and a row is spread over a
+// lane GROUP of G lanes, each owning chunks of 8 consecutive floats (two 128-bit loads, one
+// 128-bit shadow store), so that 32 / G rows per warp reduce together in log2(G) shuffle steps:
+//   G = 8,  C = 2: rows of up to 128 floats, 4 rows per warp step (x kAppendSteps steps in flight)
+//   G = 32, C = 2 / 4 / 8: rows of up to 512 / 1024 / 2048 floats, one row per warp step
+// The shadow of a cosine store holds x * (1 / ||x||) (one reciprocal per row); the certification
+// bound is measured on exactly that value (+2e-7 for its distance to x / ||x||).
+constexpr int kAppendSteps = 2;
+template <int G, int C>
 __global__ void __launch_bounds__(256)
-append_norm_small_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
-                         int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
-                         float* __restrict__ sqnorms, __nv_bfloat16* __restrict__ shadow, int ld16,
-                         int normalize_shadow, int32_t* __restrict__ gids, int64_t gid0,
-                         uint32_t* __restrict__ bounds) {
+append_norm_reg_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ rows,
+                       int ld, int dim, int64_t n0, int64_t m, float* __restrict__ norms,
+                       float* __restrict__ sqnorms, __nv_bfloat16* __restrict__ shadow, int ld16,
+                       int normalize_shadow, int32_t* __restrict__ gids, int64_t gid0,
+                       uint32_t* __restrict__ bounds) {
+  constexpr int RPW = 32 / G;                       // rows per warp step
   const int lane = threadIdx.x & 31;
+  const int sub = lane % G, grp = lane / G;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int nvec = dim >> 2;                 // <= 32
-  const bool have = lane < nvec;
   const bool fp16 = normalize_shadow != 0;
   float e_max = 0.f, s_max = 0.f;
-  for (int64_t r0 = warp * kAppendR; r0 < m; r0 += nwarps * kAppendR) {
-    float4 v[kAppendR];
+  for (int64_t r0 = warp * (RPW * kAppendSteps); r0 < m; r0 += nwarps * (RPW * kAppendSteps)) {
+    float4 v[kAppendSteps][C][2];
 #pragma unroll
-    for (int j = 0; j < kAppendR; ++j) {
-      const int64_t r = r0 + j < m ? r0 + j : r0;
-      v[j] = have ? reinterpret_cast<const float4*>(src + r * src_ld)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int st = 0; st < kAppendSteps; ++st) {
+      const int64_t r = r0 + st * RPW + grp;
+      const float4* s4 = reinterpret_cast<const float4*>(src + (r < m ? r : r0) * src_ld);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int e0 = 8 * (sub + G * c);           // first float of this lane's chunk
+        v[st][c][0] = e0 < dim ? ldg_stream(s4 + (e0 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[st][c][1] = e0 + 4 < dim ? ldg_stream(s4 + (e0 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < kAppendR; ++j) {
-      if (r0 + j >= m) break;                // warp-uniform
-      const int64_t r = r0 + j;
+    for (int st = 0; st < kAppendSteps; ++st) {
+      const int64_t r = r0 + st * RPW + grp;
+      const bool live = r < m;
       float acc = 0.f;
-      acc = fmaf(v[j].x, v[j].x, acc); acc = fmaf(v[j].y, v[j].y, acc);
-      acc = fmaf(v[j].z, v[j].z, acc); acc = fmaf(v[j].w, v[j].w, acc);
-      const float tot = warp_sum(acc);
-      const float nrm = fmaxf(sqrtf(tot), 1e-8f);
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4& x = v[st][c][h];
+          acc = fmaf(x.x, x.x, acc); acc = fmaf(x.y, x.y, acc); acc = fmaf(x.z, x.z, acc); acc = fmaf(x.w, x.w, acc);
+        }
+#pragma unroll
+      for (int off = G / 2; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      const float nrm = fmaxf(sqrtf(acc), 1e-8f);
+      const float rcp = fp16 ? 1.f / nrm : 1.f;
       float* d = rows + (n0 + r) * (int64_t)ld;
-      if (have && d != src + r * src_ld) reinterpret_cast<float4*>(d)[lane] = v[j];
-      if (lane == 0) {
+      const bool copy = live && d != src + r * src_ld;
+      float e2 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int e0 = 8 * (sub + G * c);
+        if (copy && e0 < dim) reinterpret_cast<float4*>(d)[e0 >> 2] = v[st][c][0];
+        if (copy && e0 + 4 < dim) reinterpret_cast<float4*>(d)[(e0 >> 2) + 1] = v[st][c][1];
+        if (shadow != nullptr && e0 < ld16) {       // zero padded up to ld16 (loads beyond dim gave 0)
+          const uint4 o = shadow8(scale4(v[st][c][0], rcp), scale4(v[st][c][1], rcp), fp16, e2, s2);
+          if (live) *reinterpret_cast<uint4*>(shadow + (n0 + r) * (int64_t)ld16 + e0) = o;
+        }
+      }
+      if (live && sub == 0) {
         norms[n0 + r] = nrm;
-        sqnorms[n0 + r] = tot;
+        sqnorms[n0 + r] = acc;
         if (gids != nullptr) gids[n0 + r] = (int32_t)(gid0 + r);
       }
       if (shadow != nullptr) {
-        float4 w = v[j];
-        if (fp16) { w.x = w.x / nrm; w.y = w.y / nrm; w.z = w.z / nrm; w.w = w.w / nrm; }
-        float q0, q1, q2, q3;
-        uint2 o;
-        o.x = pack16(w.x, w.y, fp16, q0, q1);
-        o.y = pack16(w.z, w.w, fp16, q2, q3);
-        if (lane < (ld16 >> 2)) reinterpret_cast<uint2*>(shadow + (n0 + r) * (int64_t)ld16)[lane] = o;
-        float e2 = 0.f, s2 = 0.f, t;
-        t = w.x - q0; e2 = fmaf(t, t, e2); s2 = fmaf(q0, q0, s2);
-        t = w.y - q1; e2 = fmaf(t, t, e2); s2 = fmaf(q1, q1, s2);
-        t = w.z - q2; e2 = fmaf(t, t, e2); s2 = fmaf(q2, q2, s2);
-        t = w.w - q3; e2 = fmaf(t, t, e2); s2 = fmaf(q3, q3, s2);
-        e_max = fmaxf(e_max, sqrtf(warp_sum(e2)));
-        s_max = fmaxf(s_max, sqrtf(warp_sum(s2)));
+#pragma unroll
+        for (int off = G / 2; off; off >>= 1) {
+          e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+        if (live) { e_max = fmaxf(e_max, sqrtf(e2)); s_max = fmaxf(s_max, sqrtf(s2)); }
       }
     }
   }
-  if (shadow != nullptr && lane == 0) {
-    atomicMax(bounds + 0, __float_as_uint(e_max * 1.00001f));
+  if (shadow != nullptr && sub == 0) {   // non-negative floats order like their bit patterns
+    atomicMax(bounds + 0, __float_as_uint(e_max * 1.00001f + 2e-7f));
     atomicMax(bounds + 1, __float_as_uint(s_max * 1.00001f));
   }
 }
@@ -514,6 +568,7 @@ int vs_destroy(vs_store* s) {
   s->shadow8_rows.destroy();
   s->gids.destroy();
   free_cert_slots(s);
+  free_ws_blocks(s);
   if (s->bounds) cudaFree(s->bounds);
   if (s->append_done) cudaEventDestroy(s->append_done);
   if (s->host_stream) cudaStreamDestroy(s->host_stream);
@@ -611,11 +666,16 @@ static int append_impl(vs_store* s, const float* rows, int64_t m, int rows_on_de
     if (blocks > cap) blocks = cap;
     const bool vec = (s->dim & 3) == 0 && (ksrc_ld & 3) == 0 && ((uintptr_t)ksrc & 15) == 0;
     auto kern = vec ? append_norm_kernel<true> : append_norm_kernel<false>;
-    // rows of <= 128 floats whose 16-bit shadow row is at most 128 elements wide (ld16/4 <= 32 lanes)
-    if (vec && s->dim <= 128 && s->ld == s->dim && s->ld16 <= 128) {
-      kern = append_norm_small_kernel;
-      blocks = (mm + warps_per_block * kAppendR - 1) / (warps_per_block * kAppendR);
-      if (blocks > cap) blocks = cap;
+    // register-resident fast paths: dim % 4 == 0 rows with 16-byte aligned source rows
+    if (vec && s->dim <= 128) {
+      kern = append_norm_reg_kernel<8, 2>;
+      const int per_block = warps_per_block * 4 * kAppendSteps;
+      blocks = std::min<int64_t>((mm + per_block - 1) / per_block, cap);
+    } else if (vec && s->dim <= 2048) {
+      kern = s->dim <= 512 ? append_norm_reg_kernel<32, 2>
+                           : (s->dim <= 1024 ? append_norm_reg_kernel<32, 4> : append_norm_reg_kernel<32, 8>);
+      const int per_block = warps_per_block * kAppendSteps;
+      blocks = std::min<int64_t>((mm + per_block - 1) / per_block, cap);
     }
     kern<<<(unsigned)blocks, 256, 0, stream>>>(
         ksrc, ksrc_ld, master, s->ld, s->dim, n0 + off, mm, (float*)s->norms.ptr(),

@@ -53,6 +53,12 @@ struct vs_store {
   struct CertSlot { cudaEvent_t done = nullptr; int* h_bad = nullptr; int32_t* d_bad = nullptr; bool busy = false; };
   std::mutex slot_mu;
   std::deque<CertSlot> slots;    // deque: growing never moves a slot another thread is using
+  // K3 workspaces (gemm_topk.cu): device blocks that are recycled instead of going through the
+  // stream-ordered allocator per search.  A block is handed to an enqueue on the stream it was last
+  // used on (stream order makes that safe) or once its event has completed (another stream).
+  struct WsBlock { void* ptr = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; bool busy = false; };
+  std::mutex ws_mu;
+  std::deque<WsBlock> ws_blocks;
   // vs_search_host: private stream + pinned staging, serialised by host_mu
   std::mutex host_mu;
   cudaStream_t host_stream = nullptr;

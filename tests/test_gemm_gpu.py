@@ -45,6 +45,9 @@ DUMP_SHAPES = [
     (700, 768, 129),       # streaming, 12 K-chunks
     (40000, 128, 256),     # many tiles per CTA: ring and accumulator phases wrap
     (30000, 384, 256),
+    (20000, 384, 700),     # streaming CTA pairs with THREE query-tile pairs per unit: an odd count once made
+                           # the epilogue groups alternate accumulator slots (mbarrier parity aliasing)
+    (20000, 128, 896),     # resident: 7 query tiles, the second CTA group holds 3
 ]
 
 
@@ -90,6 +93,7 @@ SEARCH_SHAPES = [
     (70001, 256, 200, 10),
     (66000, 384, 128, 10),     # streaming kernel
     (66000, 768, 64, 1),
+    (66000, 384, 700, 10),     # streaming, three query-tile pairs per CTA pair (odd count)
     (90000, 128, 100, 32),
     (80000, 256, 40, 100),     # top-100: kc = 200 candidates per query
     (70000, 128, 16, 128),     # largest k the path takes (kc = 256)
@@ -231,7 +235,8 @@ L2_SHAPES = [
     (70001, 128, 300, 10),     # ragged last tile: rows past the end must score -inf
     (66000, 384, 130, 10),     # streaming kernel (CTA pairs, 256-row tiles)
     (80000, 256, 40, 100),     # top-100 (config C's k)
-    (66000, 1536, 16, 100),    # config C's shape, smaller N
+    (66000, 384, 700, 10),     # streaming, three query-tile pairs per CTA pair (odd count: deadlocked once)
+    (200000, 1536, 16, 100),   # config C's shape, smaller N (enough 256-row tiles for a top-100 threshold)
 ]
 
 
@@ -254,7 +259,11 @@ def test_euclidean_gemm_search_matches_oracle(make_store, shape, dist):
     np.testing.assert_array_equal(ids, ids2)
     np.testing.assert_array_equal(scores, scores2)
     fb = int(_cabi.lib().vs_fallback_count(st._handle))
-    assert fb <= B // 4, f"{fb} of {B} queries fell back to the exact scan"
+    # U[0,1) rows at D = 1536: squared distances concentrate (sigma ~ 8 around 256) and the bf16
+    # rounding bound exceeds the rank-100 to rank-200 gap, so those queries are (correctly) handed
+    # to the exact scan; everywhere else the tensor-core path must certify most queries itself
+    if not (dist == "uniform" and d >= 1536):
+        assert fb <= B // 4, f"{fb} of {B} queries fell back to the exact scan"
 
 
 @pytest.mark.parametrize("metric", ["cosine", "euclidean"])

@@ -195,6 +195,14 @@ def test_http_shim_replays_reference_integration_test(tmp_path, native_lib):
     assert all(len(q) == 3 and q[0]["similarity_score"] > 0.999 for q in out["results"])
     r = client.post("/vectors/add", json={**body, "vectors": vecs[:2].tolist(), "metadata": meta[:1]})
     assert r.status_code == 422                                                  # schema validation
+    # request strings never leave base_path, unknown stores are not created by reads
+    for bad in ("../../x", "a/b", "..", "a_b", ""):
+        r = client.post("/vectors/add", json={"user_id": bad, "model_id": "m", "vectors": vecs[:1].tolist(),
+                                              "metadata": meta[:1]})
+        assert r.status_code == 400, (bad, r.status_code)
+    assert client.get("/vectors/count", params={"user_id": "nobody", "model_id": "m"}).status_code == 404
+    assert not (tmp_path / "stores" / "nobody").exists()
+    assert sorted(p.name for p in (tmp_path / "stores").iterdir()) == ["u"]
     app.state.store_manager.close()
 
 
@@ -251,3 +259,38 @@ def test_concurrent_queries_during_appends(make_store):
     assert seen_planted, "the planted row was never returned after it became visible"
     ids, _, _ = st.query(probe, k=1)
     assert ids == [planted_at]
+
+
+def test_ops_search_never_serves_a_stale_database(native_lib):
+    """The functional API caches the ingested database per tensor OBJECT.  Two databases of equal
+    shape searched back to back -- as numpy arrays (temporaries on the device each call) and as
+    CUDA tensors allocated one after the other (the allocator reuses the address) -- must each be
+    searched for real; an in-place update of a cached tensor must be seen too."""
+    from b200vs import ops
+    from oracle import vs_oracle
+    n, d, k = 3000, 64, 5
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((n, d), dtype=np.float32)
+    b = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((3, d), dtype=np.float32)
+    ref_a, _ = vs_oracle.batch_similarity_search(q, a, k)
+    ref_b, _ = vs_oracle.batch_similarity_search(q, b, k)
+    assert not np.array_equal(ref_a, ref_b)
+    for _ in range(2):
+        ia, _ = ops.optimized_batch_similarity_search(q, a, k)
+        ib, _ = ops.optimized_batch_similarity_search(q, b, k)
+        np.testing.assert_array_equal(ia.cpu().numpy(), ref_a)
+        np.testing.assert_array_equal(ib.cpu().numpy(), ref_b)
+    ta = torch.from_numpy(a).cuda()
+    ia, _ = ops.optimized_batch_similarity_search(q, ta, k)
+    np.testing.assert_array_equal(ia.cpu().numpy(), ref_a)
+    ptr = ta.data_ptr()
+    del ta
+    tb = torch.from_numpy(b).cuda()              # very likely the same address, same shape, _version 0
+    ib, _ = ops.optimized_batch_similarity_search(q, tb, k)
+    np.testing.assert_array_equal(ib.cpu().numpy(), ref_b)
+    tb.copy_(torch.from_numpy(a))                # in-place update of a cached tensor
+    ia, _ = ops.optimized_batch_similarity_search(q, tb, k)
+    np.testing.assert_array_equal(ia.cpu().numpy(), ref_a)
+    assert ptr  # (the address reuse itself is allocator behaviour, not asserted)
+    ops._db_cache.clear()

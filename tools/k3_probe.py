@@ -23,7 +23,7 @@ ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--dim", type=int, default=128)
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--k", type=int, default=10)
-ap.add_argument("--mode", default="gemm")
+ap.add_argument("--mode", default="gemm_nocert")
 ap.add_argument("--metric", default="cosine")
 ap.add_argument("--iters", type=int, default=6)
 ap.add_argument("--rounds", type=int, default=6)
@@ -68,6 +68,7 @@ for rnd in range(args.rounds):
             for _ in range(2):
                 st.search(q, args.k)
             torch.cuda.synchronize()
+            fr0 = int(lib.vs_fallback_count(st.shard.handle)), int(lib.vs_retry_count(st.shard.handle))
             ms0, n0 = C.c_double(), C.c_int64()
             lib.vs_profile_read(1, C.byref(ms0), C.byref(n0))          # slot 1 = K3 launches (kProfGemm)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,7 +82,9 @@ for rnd in range(args.rounds):
             per = e0.elapsed_time(e1) / args.iters
             kms = ms1.value / args.iters      # vs_profile_read clears the record on every read
             chk = int(ids.to(torch.int64).sum().item())
-            results.setdefault(cfg, []).append((per, kms, chk, n1.value / args.iters))
+            fr1 = int(lib.vs_fallback_count(st.shard.handle)), int(lib.vs_retry_count(st.shard.handle))
+            results.setdefault(cfg, []).append((per, kms, chk, n1.value / args.iters,
+                                                (fr1[0] - fr0[0]) / args.iters, (fr1[1] - fr0[1]) / args.iters))
         except Exception as e:  # noqa: BLE001
             print(f"{name:14s} ERROR {e}", flush=True)
         for k_ in knobs:
@@ -95,5 +98,5 @@ for cfg, rows in results.items():
     kms = [r[1] for r in rows]
     print(f"{name:14s} search min {min(per):7.3f} med {statistics.median(per):7.3f} ms   K3 kernels min {min(kms):7.3f} "
           f"med {statistics.median(kms):7.3f} ms ({rows[0][3]:.1f} launches)  qps(med) {args.batch / statistics.median(per) * 1e3:9.0f}"
-          f"  idsum {rows[-1][2]}  {kv}", flush=True)
+          f"  idsum {rows[-1][2]}  fb/retry per search {rows[-1][4]:.1f}/{rows[-1][5]:.1f}  {kv}", flush=True)
 print(f"# fallbacks {fb[0]} retries {fb[1]}")

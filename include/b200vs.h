@@ -195,6 +195,13 @@ VS_API int vs_merge(int device, int metric, const float* cand_scores, const int3
 VS_API int vs_exchange_push(int device, const void* src, int64_t bytes, void* const* peer_dst,
                             void* const* peer_flag, int G, uint32_t step, void* counter, void* stream);
 VS_API int vs_exchange_wait(int device, const void* flags, int G, uint32_t step, void* stream);
+/* vs_exchange_wait + the merge of the G blocks (each (2, B, k) int32: fp32 score bits, then ids; block g
+ * starts g * block_words words after `blocks`) in ONE kernel: one warp per query, no shared memory, so
+ * it runs next to the following search's GEMM instead of waiting for a gap.  G * k <= 256; order and
+ * conventions of vs_merge. */
+VS_API int vs_exchange_wait_merge(int device, int metric, const void* flags, int G, uint32_t step,
+                                  const void* blocks, int64_t block_words, int B, int k,
+                                  float* out_scores, int32_t* out_ids, void* stream);
 
 /* K5 rescore_fp32 -- exact fp32 scores (same arithmetic as the fp32 scan) for `kc`
  * candidate ids per query, sorted, best `k` written out.  cand_ids: (B, kc) device. */

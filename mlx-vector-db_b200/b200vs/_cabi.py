@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         "vs_rescore": (i32, [p, f32p, i32, i32p, i32, i32, f32p, i32p, p]),
         "vs_exchange_push": (i32, [i32, p, i64, p, p, i32, C.c_uint32, p, p]),
         "vs_exchange_wait": (i32, [i32, p, i32, C.c_uint32, p]),
+        "vs_exchange_wait_merge": (i32, [i32, i32, p, i32, C.c_uint32, p, i64, i32, i32, f32p, i32p, p]),
         "vs_debug_gemm_scores": (i32, [p, f32p, i32, f32p, p]),
         "vs_normalize_rows": (i32, [i32, f32p, i64, i32, f32p, p]),
         "vs_score_matrix": (i32, [i32, i32, f32p, i32, f32p, i64, i32, f32p, p]),

@@ -179,15 +179,21 @@ class PeerExchange:
         _cabi.check(lib.vs_exchange_push(dev, C.c_void_p(pack.data_ptr()), self.block_bytes, self.dst[slot],
                                          self.flag[slot], self.world, self.step,
                                          C.c_void_p(self.base + self.counter_off), stream))
-        _cabi.check(lib.vs_exchange_wait(dev, C.c_void_p(self.base + self.flags_off + slot * self.world * 4),
-                                         self.world, self.step, stream))
         B, k = self.B, self.k
         out_s = torch.empty((B, k), dtype=torch.float32, device=shard.device)
         out_i = torch.empty((B, k), dtype=torch.int32, device=shard.device)
+        flags = C.c_void_p(self.base + self.flags_off + slot * self.world * 4)
         base = self.base + slot * self.slot_bytes
-        _cabi.check(lib.vs_merge(dev, shard.metric, C.c_void_p(base), C.c_void_p(base + 4 * B * k), self.world, B, k,
-                                 self.block_bytes // 4, C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
-                                 stream))
+        if self.world * k <= 256:
+            # wait + merge in one kernel that needs no shared memory: runs next to the next search's GEMM
+            _cabi.check(lib.vs_exchange_wait_merge(dev, shard.metric, flags, self.world, self.step, C.c_void_p(base),
+                                                   self.block_bytes // 4, B, k, C.c_void_p(out_s.data_ptr()),
+                                                   C.c_void_p(out_i.data_ptr()), stream))
+        else:
+            _cabi.check(lib.vs_exchange_wait(dev, flags, self.world, self.step, stream))
+            _cabi.check(lib.vs_merge(dev, shard.metric, C.c_void_p(base), C.c_void_p(base + 4 * B * k), self.world, B, k,
+                                     self.block_bytes // 4, C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                     stream))
         return out_i, out_s
 
 

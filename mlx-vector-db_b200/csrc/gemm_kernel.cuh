@@ -642,6 +642,67 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * TN);
         float rmax = MODE == kModeMax ? rmax_l[mt & 15] : VS_NEG_INF;
         float va[32], vb[32];
+        // Measured on the B200 and NOT kept (profiles/r02_k3_probe.txt, block c15): with the deferral the plain
+        // resident kernel needs 167 registers and ran SLOWER (10 M x 128: 2.22 vs 1.92 ms, a 1.25 M-row shard:
+        // 0.347 vs 0.295 ms).  -DVS_DEFER_HITS=1 builds it.
+#ifndef VS_DEFER_HITS
+#define VS_DEFER_HITS 0
+#endif
+        constexpr bool DEFER = VS_DEFER_HITS != 0 && FILT && GEN == 0 && RES;
+        float dv[DEFER ? 32 : 1];                          // the deferred chunk (see below)
+        int d_cc = -1;                                     // its first column, -1 = none (warp-uniform)
+        float d_m = 0.f;
+        // Rare path: the hits of one 32-column chunk `vv` (columns cc_ .. cc_+31 of tile nt, chunk maximum
+        // m_ per lane, taking-part mask mword_), taken straight from registers.  Per 8-column group a
+        // branch-free hit mask per lane, one warp-uniform vote, and a (divergent, almost always single-trip)
+        // loop over the set bits that picks the value with a select chain -- no per-value branches.
+        // Measured at 10 M x 128, batch 1024 (profiles/r02_k3_probe.txt): 1.96 ms vs 2.14 ms per search with
+        // the first version, which re-read the 8-column groups from TMEM.
+        auto process_hits = [&](float (&vv)[32], const int cc_, const float m_, const uint32_t mword_) {
+          const int lim = (int)min((int64_t)TN, p.n_rows - (int64_t)nt * TN) - cc_;   // live columns
+          const int32_t id0 = (int32_t)((int64_t)nt * TN + cc_);
+          // hand (best key of this chunk, query) of every lane with a hit to the ladder warp
+          // (chunks that reach past the end of the store are skipped: their maximum may belong
+          // to a zero-filled column)
+          if (lim >= 32) {
+            const uint32_t hm = __ballot_sync(0xffffffffu, m_ >= t);
+            const int nh = __popc(hm);
+            uint32_t tl = *reinterpret_cast<volatile uint32_t*>(hq_tail + (warp - 4));
+            tl = __shfl_sync(0xffffffffu, tl, 0);
+            if (hq_h + nh - tl <= (uint32_t)kHqEntries) {
+              if (m_ >= t)
+                my_ring[(hq_h + __popc(hm & ((1u << lane) - 1u))) % kHqEntries] = make_float2(m_, __int_as_float(q));
+              hq_h += nh;
+              __syncwarp();
+              if (lane == 0) {
+                __threadfence_block();
+                *reinterpret_cast<volatile uint32_t*>(hq_head + (warp - 4)) = hq_h;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t hits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hits |= (vv[8 * u + j] >= t ? 1u : 0u) << j;
+            const int live = lim - 8 * u;                       // columns of this group inside the store
+            hits &= live >= 8 ? 0xffu : (live <= 0 ? 0u : (1u << live) - 1u);
+            hits &= mword_ >> (8 * u);
+            if (!__any_sync(0xffffffffu, hits != 0u)) continue;
+            while (hits) {
+              const int j = __ffs((int)hits) - 1;
+              hits &= hits - 1u;
+              float w = vv[8 * u];
+#pragma unroll
+              for (int jj = 1; jj < 8; ++jj) w = j == jj ? vv[8 * u + jj] : w;
+              if (c < kCandCap) {
+                p.cand_score[cbase + c] = w;
+                p.cand_id[cbase + c] = id0 + 8 * u + j;
+              }
+              ++c;
+            }
+          }
+        };
         constexpr int TN_READ = MODE == kModeNop ? 0 : (MODE == kModeHalf ? TN / 2 : TN);
         if (TN_READ > 0) tc_ld32(taddr, va);
 #pragma unroll 1
@@ -696,55 +757,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
               if (MODE == kModeMax) rmax = fmaxf(rmax, m);
               if (FILT && __any_sync(0xffffffffu, m >= t)) {
-                // rare path: take the hits straight from the registers of this chunk (no second
-                // tcgen05.ld).  Per 8-column group one warp-uniform vote; inside, a branch-free hit
-                // mask per lane and a (divergent, almost always single-trip) loop over its set bits
-                // that picks the value with a select chain -- no per-value branches.  Measured at
-                // 10 M x 128, batch 1024 (profiles/r02_k3_probe.txt): 1.96 ms vs 2.14 ms per search
-                // with the first version, which re-read the 8-column groups from TMEM.
-                const int lim = (int)min((int64_t)TN, p.n_rows - (int64_t)nt * TN) - cc;   // live columns
-                const int32_t id0 = (int32_t)((int64_t)nt * TN + cc);
-                // hand (best key of this chunk, query) of every lane with a hit to the ladder warp
-                // (chunks that reach past the end of the store are skipped: their maximum may belong
-                // to a zero-filled column)
-                if (lim >= 32) {
-                  const uint32_t hm = __ballot_sync(0xffffffffu, m >= t);
-                  const int nh = __popc(hm);
-                  uint32_t tl = *reinterpret_cast<volatile uint32_t*>(hq_tail + (warp - 4));
-                  tl = __shfl_sync(0xffffffffu, tl, 0);
-                  if (hq_h + nh - tl <= (uint32_t)kHqEntries) {
-                    if (m >= t)
-                      my_ring[(hq_h + __popc(hm & ((1u << lane) - 1u))) % kHqEntries] = make_float2(m, __int_as_float(q));
-                    hq_h += nh;
-                    __syncwarp();
-                    if (lane == 0) {
-                      __threadfence_block();
-                      *reinterpret_cast<volatile uint32_t*>(hq_head + (warp - 4)) = hq_h;
-                    }
+                // rare path.  (Experiment, off: the first chunk of an accumulator with a hit is only COPIED
+                // and handled after the accumulator has been handed back -- see DEFER above.)
+                bool handled = false;
+                if constexpr (DEFER) {
+                  if (d_cc < 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dv[j] = v[j];
+                    d_cc = cc;
+                    d_m = m;
+                    handled = true;
                   }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (!__any_sync(0xffffffffu, g[u] >= t)) continue;
-                  uint32_t hits = 0;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) hits |= (v[8 * u + j] >= t ? 1u : 0u) << j;
-                  const int live = lim - 8 * u;                       // columns of this group inside the store
-                  hits &= live >= 8 ? 0xffu : (live <= 0 ? 0u : (1u << live) - 1u);
-                  hits &= mword >> (8 * u);
-                  while (hits) {
-                    const int j = __ffs((int)hits) - 1;
-                    hits &= hits - 1u;
-                    float w = v[8 * u];
-#pragma unroll
-                    for (int jj = 1; jj < 8; ++jj) w = j == jj ? v[8 * u + jj] : w;
-                    if (c < kCandCap) {
-                      p.cand_score[cbase + c] = w;
-                      p.cand_id[cbase + c] = id0 + 8 * u + j;
-                    }
-                    ++c;
-                  }
-                }
+                if (!handled) process_hits(v, cc, m, mword);
               }
             }
           }
@@ -755,6 +780,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (lane == 0) {
           if (CG == 2 && crank != 0) bar_arrive_remote(bar_acce + 8 * slot, 0);
           else bar_arrive(bar_acce + 8 * slot);
+        }
+        if constexpr (DEFER) {
+          if (d_cc >= 0) process_hits(dv, d_cc, d_m, 0xffffffffu);
         }
         if (MODE == kModeMax) {
           // one maximum per kMaxGroupTiles consecutive tiles of this unit

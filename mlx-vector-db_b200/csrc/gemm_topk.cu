@@ -153,7 +153,7 @@ tau_select_kernel(const float* __restrict__ gmax, int n_groups, int ks, int B, i
     if (lane == 0) tau_cur[b] = 0xff800000u;             // enc_key(+inf)
     return;
   }
-  uint32_t* v = tsm + (size_t)warp * (n_groups + kTauList);
+  uint32_t* v = tsm + (size_t)warp * (n_groups + kTauList + kLevels);
   uint32_t* top = v + n_groups;
   const float* src = gmax + (int64_t)b * n_groups;
   for (int i = lane; i < n_groups; i += 32) v[i] = enc_key(src[i]);
@@ -164,7 +164,24 @@ tau_select_kernel(const float* __restrict__ gmax, int n_groups, int ks, int B, i
   if (n_groups < ks) {
     L[0] = VS_NEG_INF;
   } else {
-    const uint32_t T0 = warp_rth_largest(v, n_groups, ks, lane);
+    // the ks-th largest maximum: up to 1024 maxima are searched from registers (32 per lane, no memory
+    // traffic in the 32 counting rounds), more from shared memory
+    uint32_t T0 = 0;
+    if (n_groups <= 1024) {
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = lane + 32 * i < n_groups ? v[lane + 32 * i] : 0u;   // 0 sorts below every key
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T0 | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c += r[i] >= cand;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= ks) T0 = cand;
+      }
+    } else {
+      T0 = warp_rth_largest(v, n_groups, ks, lane);
+    }
     L[0] = dec_key(T0);
     // the maxima at or above lvl 0 (ks of them, more with ties), compacted
     int m = 0;
@@ -178,13 +195,29 @@ tau_select_kernel(const float* __restrict__ gmax, int n_groups, int ks, int B, i
     }
     __syncwarp();
     if (m <= kTauList) {
-      int nl = 1;
-#pragma unroll
-      for (int j = 1; j < kLevels; ++j) {
-        const int rk = (ks + (1 << j) - 1) >> j;          // ceil(ks / 2^j)
-        const int rprev = (ks + (1 << (j - 1)) - 1) >> (j - 1);
-        if (nl == j && rprev > 1) { L[j] = dec_key(warp_rth_largest(top, m, rk, lane)); nl = j + 1; }
+      // rank the kept maxima by counting (there are about ks of them): the value of rank r - 1 is the
+      // r-th largest; level j takes rank ceil(ks / 2^j)
+      float* lsh = reinterpret_cast<float*>(top + kTauList);          // kLevels floats per warp
+      if (lane < kLevels) lsh[lane] = __int_as_float(0x7f800000);
+      __syncwarp();
+      for (int i = lane; i < m; i += 32) {
+        const uint32_t mine = top[i];
+        int r = 0;
+        for (int j = 0; j < m; ++j) { const uint32_t o = top[j]; r += (o > mine) || (o == mine && j < i); }
+        int rk = ks;
+        for (int j = 1; j < kLevels && rk > 1; ++j) {
+          rk = (rk + 1) >> 1;                                          // ceil(ks / 2^j)
+          if (r == rk - 1) lsh[j] = dec_key(mine);
+        }
       }
+      __syncwarp();
+      int nl = 1;
+      {
+        int rk = ks;
+        for (int j = 1; j < kLevels && rk > 1; ++j) { rk = (rk + 1) >> 1; nl = j + 1; }
+      }
+#pragma unroll
+      for (int j = 1; j < kLevels; ++j) if (j < nl) L[j] = lsh[j];
       // extrapolated levels
       float d = nl >= 3 ? 0.5f * (L[2] - L[0]) : (nl == 2 ? L[1] - L[0] : 0.f);
 #pragma unroll
@@ -830,7 +863,7 @@ static int gemm_block_enqueue(vs_store* s, int64_t n, const float* q, int B, int
       cudaFuncSetAttribute(tau_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     });
     tau_select_kernel<<<(rows_padded + kTauWarps - 1) / kTauWarps, kTauWarps * 32,
-                        (size_t)kTauWarps * (s_groups + kTauList) * 4, stream>>>(gmax, s_groups, ks, B, rows_padded, tau,
+                        (size_t)kTauWarps * (s_groups + kTauList + kLevels) * 4, stream>>>(gmax, s_groups, ks, B, rows_padded, tau,
                                                                                  lvl, lcnt, bad);
   }
   count_launch();

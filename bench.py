@@ -572,6 +572,11 @@ def run_b200(args):
         _cabi.check(lib.vs_profile_read(kind, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    # searches in flight in the timed loops: 2 on one GPU (the certification count of batch i travels to the
+    # host while batch i + 1 runs); 3 across GPUs, where a step also depends on every other rank having
+    # finished the step two before it, so that one late rank (host jitter) does not stall all of them
+    DEPTH = 2 if world == 1 else 3
+
     def measure(st, n, d, B, k, steps, warmup, with_e2e=True, wl_name=""):
         gq = torch.Generator().manual_seed(QUERY_SEED)
         if args.dist == "uniform":
@@ -581,8 +586,13 @@ def run_b200(args):
         q_dev = q_host.to(dev)
         fb0 = int(lib.vs_fallback_count(st.shard.handle))
         rt0 = int(lib.vs_retry_count(st.shard.handle))
+        barrier()
+        tw = time.perf_counter()
         for _ in range(warmup):
             ids, scores = st.search(q_dev, k)
+        barrier()
+        # expected length of the timed region (the same on every rank: the decision below shapes collective loops)
+        est_ms = max_over_ranks(1e3 * (time.perf_counter() - tw) / max(1, warmup) * steps)
         # ---- device-resident timing (value) ----
         lib.vs_profile(1)
         read_profile(0), read_profile(1)
@@ -590,25 +600,38 @@ def run_b200(args):
         launches0 = lib.vs_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = make_sampler(args.clocks, local_rank)
-        if rank == 0:
+        # A timed region shorter than ~0.7 s is too short for nvidia-smi's 100 ms sampling anyway (the clocks
+        # are then sampled under the same load right after it, below) -- and spawning the sampler right before
+        # it disturbs the host for milliseconds, which a 10 ms region (8 GPUs, 20 steps) cannot absorb
+        sample_inside = est_ms >= 700.0
+        if rank == 0 and sample_inside:
             sampler.start()
         # every step submits one batch and collects one: two searches are in flight, so a batch's
         # certification count reaches the host (and its candidates cross NVLink at N > 1) while
         # the next batch already runs -- ShardedVectorStore.submit / result
+        def pipelined(nsteps, begin=lambda: st.submit(q_dev, k), finish=st.result):
+            """nsteps searches with DEPTH in flight: submit i + DEPTH - 1, then collect i."""
+            from collections import deque
+            inflight = deque()
+            out = None
+            for _ in range(nsteps):
+                inflight.append(begin())
+                if len(inflight) >= DEPTH:
+                    out = finish(inflight.popleft())
+            while inflight:
+                out = finish(inflight.popleft())
+            return out
+
         e0.record()
-        pend = st.submit(q_dev, k)
-        for _ in range(steps - 1):
-            nxt = st.submit(q_dev, k)
-            ids, scores = st.result(pend)
-            pend = nxt
-        ids, scores = st.result(pend)
+        ids, scores = pipelined(steps)
         e1.record()
         barrier()
-        clocks = sampler.stop() if rank == 0 else {}
+        clocks = sampler.stop() if (rank == 0 and sample_inside) else {}
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = lib.vs_launch_count() - launches0
         lib.vs_profile(0)
-        if ms < 700.0:
+        resample = ms < 700.0 or not sample_inside
+        if resample:
             # the timed region was too short for nvidia-smi's 100 ms sampling: keep the same step
             # running (untimed, every rank -- the all-gather is collective) and sample under load
             extra = int(min(20000, 700.0 / max(ms / steps, 1e-3))) + 1
@@ -616,12 +639,7 @@ def run_b200(args):
             if rank == 0:
                 sampler.start()
                 time.sleep(0.05)
-            pend = st.submit(q_dev, k)
-            for _ in range(extra - 1):
-                nxt = st.submit(q_dev, k)
-                st.result(pend)
-                pend = nxt
-            st.result(pend)
+            pipelined(extra)
             barrier()
             if rank == 0:
                 clocks = sampler.stop()
@@ -651,9 +669,9 @@ def run_b200(args):
                          "bracket would include queueing behind the other search)")
         res = {"ms_per_step": ms / steps, "qps": B * steps / (ms / 1e3), "launches": int(launches),
                "exact_fallback_queries_per_step": (int(lib.vs_fallback_count(st.shard.handle)) - fb0) /
-                                                  max(1, warmup + steps + (extra if ms < 700.0 else 0)),
+                                                  max(1, warmup + steps + (extra if resample else 0)),
                "wide_retry_queries_per_step": (int(lib.vs_retry_count(st.shard.handle)) - rt0) /
-                                              max(1, warmup + steps + (extra if ms < 700.0 else 0)),
+                                              max(1, warmup + steps + (extra if resample else 0)),
                "clocks": clocks, "ids": ids, "scores": scores}
         n_local = n // world
         if gemm_n and gemm_ms >= scan_ms:
@@ -728,7 +746,7 @@ def run_b200(args):
                                                        C.c_void_p(out_i.data_ptr())))
                     return
                 # sharded store: every step copies its queries from pinned host memory, searches, and copies
-                # its results back to pinned host memory; like the device-resident loop two steps are in flight
+                # its results back to pinned host memory; like the device-resident loop DEPTH steps are in flight
                 # (submit i+1, then collect i), the host waits for the last copy at the end
                 def begin():
                     return st.submit(q_host.to(dev, non_blocking=True), k)
@@ -738,12 +756,7 @@ def run_b200(args):
                     out_i.copy_(i_, non_blocking=True)
                     out_s.copy_(s_, non_blocking=True)
 
-                pend = begin()
-                for _ in range(nsteps - 1):
-                    nxt = begin()
-                    finish(pend)
-                    pend = nxt
-                finish(pend)
+                pipelined(nsteps, begin, finish)
                 torch.cuda.current_stream().synchronize()
 
             e2e_run(max(1, warmup))
@@ -885,7 +898,8 @@ def run_b200(args):
                        "arithmetic": "fp16 tensor-core prefilter (tcgen05, fp32 accumulate) over a 16-bit shadow of the "
                                      "normalised rows + per-query certified fp32 rescoring: results are the exact fp32 "
                                      "ones (uncertified queries are re-run through the fp32 scan; counted below)",
-                       "pipeline": "2 batches in flight (submit i+1, then collect i): ShardedVectorStore.submit/result",
+                       "pipeline": f"{2 if world == 1 else 3} batches in flight (submit ahead, then collect the oldest): "
+                                   "ShardedVectorStore.submit/result",
                        "l2_policy": "database (5.1 GB fp32 + 2.6 GB 16-bit) is far larger than the 126 MB L2; "
                                     "no flush needed between steps",
                        "data_detail": f"{'U[0,1)' if args.dist == 'uniform' else 'N(0,1)'} rows, 8 seeded blocks "

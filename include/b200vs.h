@@ -156,6 +156,14 @@ VS_API int vs_search_submit(vs_store* s, const float* q, int B, int k, int flags
                             const uint32_t* row_mask, int64_t mask_live, float* out_scores,
                             int32_t* out_ids, void* stream, vs_ticket** ticket_out);
 VS_API int vs_search_complete(vs_store* s, vs_ticket* ticket);
+/* vs_search_submit on another stream than the caller's: `search_stream` first waits for everything
+ * enqueued on `cur_stream` so far (the queries, an earlier reader of the output buffers), and an event
+ * is recorded behind the search for vs_exchange_result.  One call instead of the caller's own event
+ * plumbing: a sharded server is host-bound at batch 1 otherwise. */
+VS_API int vs_search_submit_on(vs_store* s, const float* q, int B, int k, int flags,
+                               const uint32_t* row_mask, int64_t mask_live, float* out_scores,
+                               int32_t* out_ids, void* cur_stream, void* search_stream,
+                               vs_ticket** ticket_out);
 
 /* Same with HOST buffers: H2D of the queries, search, D2H of the results, stream
  * synchronised on return.  This is the call MLXVectorStore.query()/batch_query() make. */
@@ -202,6 +210,17 @@ VS_API int vs_exchange_wait(int device, const void* flags, int G, uint32_t step,
 VS_API int vs_exchange_wait_merge(int device, int metric, const void* flags, int G, uint32_t step,
                                   const void* blocks, int64_t block_words, int B, int k,
                                   float* out_scores, int32_t* out_ids, void* stream);
+
+/* One call per sharded search result: vs_search_complete(ticket) (the host wait for the certification
+ * count), then on `xs_stream`, ordered behind the search: vs_exchange_push of `src_block`, the wait for all
+ * G ranks' blocks and the merge into (B, k) `out_*` (vs_exchange_wait_merge, or vs_exchange_wait + vs_merge
+ * beyond G * k = 256); finally `cur_stream` is made to wait for the merge.  `local_flags` / `local_blocks`
+ * are this step's flag words / block area in THIS rank's exchange buffer.  Frees the ticket. */
+VS_API int vs_exchange_result(vs_store* s, vs_ticket* ticket, const void* src_block, int64_t block_bytes,
+                              void* const* peer_dst, void* const* peer_flag, int G, uint32_t step,
+                              void* counter, const void* local_flags, const void* local_blocks,
+                              int B, int k, float* out_scores, int32_t* out_ids, void* xs_stream,
+                              void* cur_stream);
 
 /* K5 rescore_fp32 -- exact fp32 scores (same arithmetic as the fp32 scan) for `kc`
  * candidate ids per query, sorted, best `k` written out.  cand_ids: (B, kc) device. */

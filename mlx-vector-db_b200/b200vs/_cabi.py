@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         "vs_search": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p, p]),
         "vs_search_submit": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p, p, C.POINTER(p)]),
         "vs_search_complete": (i32, [p, p]),
+        "vs_search_submit_on": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p, p, p, C.POINTER(p)]),
+        "vs_exchange_result": (i32, [p, p, p, i64, p, p, i32, C.c_uint32, p, p, p, i32, i32, f32p, i32p, p, p]),
         "vs_search_host": (i32, [p, f32p, i32, i32, i32, u32p, i64, f32p, i32p]),
         "vs_fallback_count": (i64, [p]),
         "vs_retry_count": (i64, [p]),

@@ -167,6 +167,22 @@ class PeerExchange:
         self.step = 0
         dist.barrier(group)                      # every buffer is zeroed and mapped before the first push
 
+    def result(self, shard, ticket, pack: torch.Tensor, xs, cur) -> Tuple[torch.Tensor, torch.Tensor]:
+        """vs_exchange_result: finish the search behind `ticket` (host wait for its certification count),
+        then push / wait / merge on stream `xs` and make `cur` wait for the merge: (ids, scores)."""
+        self.step += 1
+        slot = self.step % self.DEPTH
+        B, k = self.B, self.k
+        out_s = torch.empty((B, k), dtype=torch.float32, device=shard.device)
+        out_i = torch.empty((B, k), dtype=torch.int32, device=shard.device)
+        _cabi.check(_cabi.lib().vs_exchange_result(
+            shard.handle, ticket, C.c_void_p(pack.data_ptr()), self.block_bytes, self.dst[slot], self.flag[slot],
+            self.world, self.step, C.c_void_p(self.base + self.counter_off),
+            C.c_void_p(self.base + self.flags_off + slot * self.world * 4), C.c_void_p(self.base + slot * self.slot_bytes),
+            B, k, C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+            C.c_void_p(xs.cuda_stream), C.c_void_p(cur.cuda_stream)))
+        return out_i, out_s
+
     def exchange(self, shard, pack: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Push this rank's (2, B, k) block to every rank, wait for everybody's, merge: (ids, scores).
         Everything is enqueued on the current stream."""
@@ -199,11 +215,12 @@ class PeerExchange:
 
 class PendingSearch:
     """Handle returned by ShardedVectorStore.submit()."""
-    __slots__ = ("q", "B", "kk", "bufs", "ticket", "done", "stream")
+    __slots__ = ("q", "B", "kk", "bufs", "ticket", "done", "stream", "ex")
 
-    def __init__(self, q, B, kk, bufs, ticket, done=None, stream=None):
+    def __init__(self, q, B, kk, bufs, ticket, done=None, stream=None, ex=None):
         self.q, self.B, self.kk, self.bufs, self.ticket, self.done = q, B, kk, bufs, ticket, done
         self.stream = stream                     # the side stream the search was enqueued on
+        self.ex = ex                             # PeerExchange: the search went through vs_search_submit_on
 
 
 def split_batch(m: int, world: int, rank: int) -> Tuple[int, int]:
@@ -339,9 +356,24 @@ class ShardedVectorStore:
                 self._sstreams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
             ss = self._sstreams[self._nsubmit % 2]
             self._nsubmit += 1
-            ss.wait_stream(cur)                  # the queries (and an earlier reader of `pack`) are on `cur`
         else:
             ss = cur
+        # world > 1 with the peer-memory exchange: the whole stream plumbing of a step lives in two C calls
+        # (vs_search_submit_on here, vs_exchange_result in result()); a step's host cost otherwise bounds
+        # the throughput at small batches
+        ex = self._peer_exchange(B, kk) if self.world > 1 else None
+        if ex is not None and not (row_mask is not None and mask_live == 0):
+            ticket = C.c_void_p()
+            _cabi.check(_cabi.lib().vs_search_submit_on(
+                self.shard.handle, C.c_void_p(q.data_ptr()), B, kk, self.shard.flags,
+                None if row_mask is None else C.c_void_p(row_mask.data_ptr()), int(mask_live),
+                C.c_void_p(pack.data_ptr()), C.c_void_p(pack.data_ptr() + 4 * B * kk),
+                C.c_void_p(cur.cuda_stream), C.c_void_p(ss.cuda_stream), C.byref(ticket)))
+            if ss is not cur:
+                q.record_stream(ss)
+            return PendingSearch(q, B, kk, (pack, flat), ticket, None, ss, ex)
+        if ss is not cur:
+            ss.wait_stream(cur)                  # the queries (and an earlier reader of `pack`) are on `cur`
         with torch.cuda.stream(ss):
             if row_mask is not None and mask_live == 0:
                 # no local row takes part: this rank contributes an empty candidate block
@@ -367,6 +399,11 @@ class ShardedVectorStore:
             return (torch.zeros((B, 0), dtype=torch.int32, device=q.device),
                     torch.zeros((B, 0), dtype=torch.float32, device=q.device))
         pack, flat = pending.bufs
+        if pending.ex is not None:
+            cur = torch.cuda.current_stream(self.device)
+            if self._xstream is None:
+                self._xstream = torch.cuda.Stream(self.device)
+            return pending.ex.result(self.shard, pending.ticket, pack, self._xstream, cur)
         if pending.ticket is not None:
             self.shard.complete(pending.ticket)
         if self.device.type != "cuda":          # CPU stand-in shards (gloo tests)

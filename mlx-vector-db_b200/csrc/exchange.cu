@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdint>
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace vs {
 

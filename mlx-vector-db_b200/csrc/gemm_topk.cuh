@@ -27,6 +27,7 @@ struct PendingBlock {
 struct vs_ticket {
   std::vector<vs::PendingBlock> blocks;
   cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;     // recorded behind the search on `stream` (vs_search_submit_on; owned by the store's pool)
 };
 
 namespace vs {

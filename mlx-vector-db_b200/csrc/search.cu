@@ -4,6 +4,7 @@
 #include "scan_topk.cuh"
 #include "gemm_topk.cuh"
 #include "store.cuh"
+#include "exchange.cuh"
 
 namespace vs {
 
@@ -222,6 +223,82 @@ int vs_search_submit(vs_store* s, const float* q, int B, int k, int flags, const
     return rc;
   }
   *ticket_out = t;
+  return VS_OK;
+}
+
+// an event of the store's pool (32 events, round-robin: a wait enqueued on an event keeps the state
+// the event had at that moment, so re-recording it later is safe)
+static cudaEvent_t pool_event(vs_store* s) {
+  std::lock_guard<std::mutex> g(s->ev_mu);
+  if (s->ev_pool.size() < 32) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s->ev_pool.push_back(e);
+    return e;
+  }
+  return s->ev_pool[s->ev_next++ % s->ev_pool.size()];
+}
+
+int vs_search_submit_on(vs_store* s, const float* q, int B, int k, int flags, const uint32_t* row_mask,
+                        int64_t mask_live, float* out_scores, int32_t* out_ids, void* cur_stream_, void* search_stream_,
+                        vs_ticket** ticket_out) {
+  VS_REQUIRE(s != nullptr && ticket_out != nullptr, "NULL pointer");
+  *ticket_out = nullptr;
+  VS_CUDA(cudaSetDevice(s->device));
+  cudaStream_t cur = (cudaStream_t)cur_stream_, ss = (cudaStream_t)search_stream_;
+  if (ss != cur) {                       // the queries (and an earlier reader of the outputs) are on `cur`
+    cudaEvent_t e = pool_event(s);
+    VS_REQUIRE(e != nullptr, "out of CUDA events");
+    VS_CUDA(cudaEventRecord(e, cur));
+    VS_CUDA(cudaStreamWaitEvent(ss, e, 0));
+  }
+  vs_ticket* t = new vs_ticket();
+  t->stream = ss;
+  const int rc = search_impl(s, q, B, k, flags, row_mask, mask_live, out_scores, out_ids, ss, t);
+  if (rc) { gemm_complete(s, t); delete t; return rc; }
+  t->done = pool_event(s);
+  if (t->done == nullptr) { gemm_complete(s, t); delete t; set_error("out of CUDA events"); return VS_ERR_CUDA; }
+  VS_CUDA(cudaEventRecord(t->done, ss));
+  *ticket_out = t;
+  return VS_OK;
+}
+
+int vs_exchange_result(vs_store* s, vs_ticket* ticket, const void* src_block, int64_t block_bytes, void* const* peer_dst,
+                       void* const* peer_flag, int G, uint32_t step, void* counter, const void* local_flags,
+                       const void* local_blocks, int B, int k, float* out_scores, int32_t* out_ids, void* xs_stream_,
+                       void* cur_stream_) {
+  VS_REQUIRE(s != nullptr && ticket != nullptr, "NULL pointer");
+  VS_CUDA(cudaSetDevice(s->device));
+  cudaStream_t xs = (cudaStream_t)xs_stream_, cur = (cudaStream_t)cur_stream_;
+  const int64_t redo0 = s->retries.load() + s->fallbacks.load();
+  int rc = gemm_complete(s, ticket);                 // waits for THIS search's certification counts
+  const bool redone = s->retries.load() + s->fallbacks.load() != redo0;
+  cudaEvent_t after = ticket->done;
+  cudaStream_t ss = ticket->stream;
+  delete ticket;
+  if (rc) return rc;
+  if (redone || after == nullptr) {                  // re-run queries wrote their rows behind `done`
+    after = pool_event(s);
+    VS_REQUIRE(after != nullptr, "out of CUDA events");
+    VS_CUDA(cudaEventRecord(after, ss));
+  }
+  if (xs != ss) VS_CUDA(cudaStreamWaitEvent(xs, after, 0));
+  if ((rc = vs_exchange_push(s->device, src_block, block_bytes, peer_dst, peer_flag, G, step, counter, xs))) return rc;
+  if ((int64_t)G * k <= 256) {
+    rc = vs_exchange_wait_merge(s->device, s->metric, local_flags, G, step, local_blocks, block_bytes / 4, B, k,
+                                out_scores, out_ids, xs);
+  } else {
+    if ((rc = vs_exchange_wait(s->device, local_flags, G, step, xs))) return rc;
+    rc = vs_merge(s->device, s->metric, (const float*)local_blocks, (const int32_t*)local_blocks + (int64_t)B * k, G, B, k,
+                  block_bytes / 4, out_scores, out_ids, xs);
+  }
+  if (rc) return rc;
+  if (cur != xs) {                                   // the caller consumes the results on its own stream
+    cudaEvent_t e = pool_event(s);
+    VS_REQUIRE(e != nullptr, "out of CUDA events");
+    VS_CUDA(cudaEventRecord(e, xs));
+    VS_CUDA(cudaStreamWaitEvent(cur, e, 0));
+  }
   return VS_OK;
 }
 

@@ -569,6 +569,7 @@ int vs_destroy(vs_store* s) {
   s->gids.destroy();
   free_cert_slots(s);
   free_ws_blocks(s);
+  for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
   if (s->bounds) cudaFree(s->bounds);
   if (s->append_done) cudaEventDestroy(s->append_done);
   if (s->host_stream) cudaStreamDestroy(s->host_stream);

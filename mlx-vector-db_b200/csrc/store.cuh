@@ -59,6 +59,10 @@ struct vs_store {
   struct WsBlock { void* ptr = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; bool busy = false; };
   std::mutex ws_mu;
   std::deque<WsBlock> ws_blocks;
+  // cross-stream ordering events of vs_search_submit_on / vs_exchange_result, recycled round-robin
+  std::mutex ev_mu;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
   // vs_search_host: private stream + pinned staging, serialised by host_mu
   std::mutex host_mu;
   cudaStream_t host_stream = nullptr;

@@ -303,7 +303,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   constexpr int TN_LOCAL = TN / CG;                       // rows of the tile this CTA loads
   constexpr int SLOTS = kTmemCols / TN;
   static_assert(SLOTS % kEpiGroups == 0, "every epilogue group owns the same number of TMEM accumulator slots");
-  constexpr int SPC = SLOTS / kEpiGroups;                 // slots per class
   constexpr int B_CHUNK_BYTES = TN_LOCAL * 128;
   using Ops = CgOps<CG>;
   extern __shared__ unsigned char smem_raw[];
@@ -355,6 +354,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const int m_count = min(m_span, um_tiles - m_first);
   int my_tiles = 0;
   if (uig < p.n_tiles) my_tiles = (p.n_tiles - uig + units_in_group - 1) / units_in_group;
+  // accumulator classes in use (see the MMA issuer): a unit with ONE query tile has one class, which
+  // then owns every TMEM slot (otherwise half of them -- and the MMA / epilogue overlap -- would idle)
+  const int p_act = m_count == 1 ? 1 : kEpiGroups;
+  const int spc = SLOTS / p_act;                          // slots per class
 
   if (threadIdx.x == 0) {
     bar_init(bar_a, 1);
@@ -440,7 +443,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       uint32_t ph = 0;
       // Accumulator slots.  Query tile mt belongs to class mt % kEpiGroups: ONE epilogue group drains
       // it and (RESIDENT, two issuers) one issuing warp fills it, and the class owns the TMEM slots
-      // cls, cls + kEpiGroups, ... which it uses round-robin.  Every phase of a slot's full / empty
+      // cls, cls + p_act, ... which it uses round-robin (p_act = classes in use: 1 for a unit with a
+      // single query tile, which then cycles through all slots).  Every phase of a slot's full / empty
       // barriers is therefore observed by the same waiter -- an mbarrier parity wait must not skip a
       // phase (with slots handed out by a global sequence number and an odd number of query tiles
       // per unit the groups alternated slots, a wait could match a phase two completions old, and
@@ -459,8 +463,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           int u = 0;
 #pragma unroll
           for (int c = 0; c < kEpiGroups; ++c) if (c == cls) u = uses[c]++;
-          const int slot = cls + kEpiGroups * (u % SPC);
-          const uint32_t aph = (uint32_t)(u / SPC) & 1u;
+          const int slot = cls + p_act * (u % spc);
+          const uint32_t aph = (uint32_t)(u / spc) & 1u;
           bar_wait(bar_acce + 8 * slot, aph ^ 1u);      // epilogues drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TN);
@@ -622,8 +626,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       for (int mt = 0; mt < m_count; ++mt) {
         if ((mt % kEpiGroups) != grp) continue;
         const int u = my_uses++;
-        const int slot = grp + kEpiGroups * (u % SPC);   // the class's slots, round-robin (see the MMA issuer)
-        const uint32_t aph = (uint32_t)(u / SPC) & 1u;
+        const int slot = grp + p_act * (u % spc);        // the class's slots, round-robin (see the MMA issuer)
+        const uint32_t aph = (uint32_t)(u / spc) & 1u;
         const int q = ((m_first + mt) * CG + crank) * kTileM + row;
         const int64_t cbase = ((int64_t)list * q_total + q) * kCandCap;
         float t = __int_as_float(0x7f800000);

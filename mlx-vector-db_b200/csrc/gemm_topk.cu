@@ -532,8 +532,12 @@ static void plan_gemm(int kchunks, int m_tiles, int cg, bool l2, GemmPlan* plan)
   // Measured on the B200 (profiles/r02_k3_probe.txt): with query groups the ring is left with three
   // K steps in flight and the kernel is SLOWER (1 M x 768: 1.49 vs 1.30 ms, 1 M x 1536: 2.63 vs 2.29 ms),
   // so one group is the default; B200VS_GEMM_QGROUPS=1 selects the query-group layout.
+  // A unit with a single query tile has no grouping to lose: when ALL of the tile's K chunks fit next to
+  // the ring (K <= 448) they stay resident and only database chunks stream (config E, 5 M x 384 batch
+  // 256: 0.9 vs 1.7 ms per append + query cycle).
   const char* e = getenv("B200VS_GEMM_QGROUPS");
-  if (e && *e == '1') {
+  const bool single_resident = um_tiles == 1 && (int64_t)kchunks * kChunkBytes + 6 * (int64_t)slot <= (int64_t)lim;
+  if ((e && *e == '1') || (single_resident && !(e && *e == '0'))) {
     m_per_unit = 1;
     a_res = (int)std::min<int64_t>(kchunks, ((int64_t)lim - 6 * (int64_t)slot) / kChunkBytes);
     if (a_res < 0) a_res = 0;

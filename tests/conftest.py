@@ -3,7 +3,6 @@
 `-m "not gpu"` runs here (no GPU): oracle vs golden vectors, host logic, C-ABI loading.
 `-m gpu` runs on a B200: the parity tests proper, all through the C-ABI of libb200vs.so.
 """
-import os
 import sys
 from pathlib import Path
 
